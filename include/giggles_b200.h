@@ -1,0 +1,168 @@
+/*
+ * giggles_b200.h — C ABI of the B200-native GenotypeHMM forward-backward.
+ *
+ * This is the drop-in boundary.  The reference binds C++ classes
+ * straight into Cython (giggles/cpp.pxd:14-125) and has no C ABI; the entry
+ * points below are what a C-ABI rebinding of that one path needs.  Each
+ * function names the reference interface it replaces (paths are relative to
+ * the reference checkout).
+ *
+ * Plain pointers and sizes only.  No torch / C++ types.  All functions are
+ * synchronous, keep no global state apart from the CUDA context, return 0 on
+ * success and a non-zero gg_status plus a message in `err` on failure (the
+ * C++ shim `GenotypeHMM` re-throws that as std::runtime_error so Cython's
+ * `except +` behaviour of cpp.pxd:100-103 is kept).
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with GG_ERR_NO_DEVICE.
+ */
+#ifndef GIGGLES_B200_H
+#define GIGGLES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_MAX_ALLELES 16   /* giggles/vcf.py:406 caps alleles per site      */
+#define GG_MAX_UNTAGGED 24  /* 2^u bipartitions per column; u_c <= max_cov   */
+
+typedef enum gg_status {
+    GG_OK = 0,
+    GG_ERR_INVALID = 1,    /* malformed problem (unsorted reads, bad index…)  */
+    GG_ERR_NO_DEVICE = 2,  /* no CUDA device / driver                         */
+    GG_ERR_CUDA = 3,       /* a CUDA call failed                              */
+    GG_ERR_NOMEM = 4,      /* problem does not fit the device memory budget   */
+    GG_ERR_UNSUPPORTED = 5
+} gg_status;
+
+/*
+ * One chromosome's worth of input to GenotypeHMM::GenotypeHMM
+ * (src/genotypehmm.cpp:19-51, ctor declared at src/genotypehmm.h:142), flattened
+ * to structure-of-arrays.  Column c is VCF position positions[c]
+ * (giggles/cli/genotype.py:265: every position of the chromosome is a column).
+ *
+ * Reads are in ReadSet order (src/readset.h:41-68: sorted by first position);
+ * read k's entries are entry_*[read_entry_offset[k] .. read_entry_offset[k+1]).
+ * entry_column must be strictly increasing inside a read (src/read.cpp:74-83)
+ * and the first column non-decreasing across reads (src/columniterator.cpp:28-35).
+ * Every read needs at least one entry (src/read.cpp:86-88 throws otherwise).
+ *
+ * entry_em holds the NORMALISED emission probabilities the reference keeps in
+ * Entry::emission_score (src/entry.cpp:50-64); use gg_entry_emission() to get
+ * them from raw alignment scores.  entry_em_offset[e+1]-entry_em_offset[e]
+ * must be >= n_alleles[entry_column[e]].  An entry with entry_allele == -1 is
+ * skipped by the emission product but its read still occupies a bipartition
+ * bit (src/genotypehmm.cpp:583,612; src/columniterator.cpp:132-137).
+ */
+typedef struct gg_problem {
+    uint32_t n_columns;               /* C                                      */
+    uint32_t n_haps;                  /* R = n_references (genotypehmm.h:44)    */
+    const uint32_t *positions;        /* [C] strictly increasing; may be NULL   */
+    const uint32_t *n_alleles;        /* [C] 1..GG_MAX_ALLELES                  */
+    const int32_t *allele_ref;        /* [C*R] panel allele of haplotype h at c, -1 = missing */
+    const float *recomb;              /* [>= C-1] recombcost, fp32 like genotypehmm.h:62; step c-1 -> c uses recomb[c-1] */
+    uint32_t n_reads;                 /* N                                      */
+    const int8_t *read_tag;           /* [N] -1 untagged, 0 = H1, 1 = H2 (src/read.cpp:45-51) */
+    const uint32_t *read_entry_offset;/* [N+1] CSR                              */
+    const uint32_t *entry_column;     /* [E] column index of the entry          */
+    const int32_t *entry_allele;      /* [E] observed allele, -1 = none         */
+    const uint64_t *entry_em_offset;  /* [E+1] offsets into entry_em            */
+    const double *entry_em;           /* normalised emission probabilities      */
+} gg_problem;
+
+typedef struct gg_options {
+    int32_t device;                   /* CUDA ordinal; -1 = current device      */
+    uint64_t state_budget_bytes;      /* HBM budget for alpha/beta columns; 0 = 80 % of free memory */
+    int32_t kernel_variant;           /* 0 = auto; >0 forces a kernel variant (tests/profiling) */
+    int32_t reserved;
+} gg_options;
+
+typedef struct gg_result gg_result;   /* host-side result table                 */
+typedef struct gg_hmm gg_hmm;         /* device-resident problem + schedule     */
+
+/* Sweep statistics; `algorithmic_bytes` follows SURVEY §8(d): 20 B per state per column. */
+typedef struct gg_stats {
+    uint64_t n_columns;
+    uint64_t state_columns;           /* sum_c 2^{u_c} R^2                      */
+    uint64_t algorithmic_bytes;       /* 20 * state_columns                     */
+    uint64_t scheduled_bytes;         /* bytes the schedule really moves (incl. checkpoint recompute) */
+    uint64_t n_launches;              /* kernels launched by one gg_hmm_sweep   */
+    uint64_t n_backward_steps;        /* column steps incl. recompute           */
+    uint64_t n_forward_steps;
+    uint64_t state_bytes_reserved;    /* arena size                             */
+    uint32_t max_untagged;            /* max_c u_c                              */
+    uint32_t checkpoint_levels;
+    float last_sweep_ms;              /* CUDA-event time of the last sweep      */
+    float last_fwdbwd_kernel_ms;      /* summed time of the column-step kernels in the last timed sweep (0 if not timed) */
+} gg_stats;
+
+/* ---- one-shot call: replaces `new GenotypeHMM(...)` (giggles/core.pyx:498 ->
+ *      src/genotypehmm.cpp:19-51).  Host buffers in, host result out; the H2D
+ *      and D2H copies happen inside. */
+int gg_hmm_run(const gg_problem *p, const gg_options *o, gg_result **out,
+               char *err, size_t errlen);
+
+/* ---- staged form of the same call, for callers that keep the problem resident
+ *      (bench.py times gg_hmm_sweep alone; gg_hmm_run = create+sweep+fetch+destroy). */
+int gg_hmm_create(const gg_problem *p, const gg_options *o, gg_hmm **out,
+                  char *err, size_t errlen);          /* plan + H2D             */
+int gg_hmm_sweep(gg_hmm *h, int timed_kernels, char *err, size_t errlen); /* backward + forward + posterior on device */
+int gg_hmm_fetch(gg_hmm *h, gg_result **out, char *err, size_t errlen);    /* D2H posteriors        */
+int gg_hmm_stats(const gg_hmm *h, gg_stats *s);
+void gg_hmm_destroy(gg_hmm *h);
+
+/* ---- result access: replaces GenotypeHMM::get_genotype_likelihoods
+ *      (src/genotypehmm.cpp:563-574, giggles/core.pyx:505-506).  Returns a pointer
+ *      to n_genotypes = n_alleles(n_alleles+1)/2 doubles that sum to 1, indexed by
+ *      the reference's ordered-pair genotype index a1 + a2(a2+1)/2
+ *      (src/genotypehmm.cpp:524-528).  NULL if column is out of range. */
+const double *gg_result_likelihoods(const gg_result *r, uint32_t column, uint32_t *n_genotypes);
+uint32_t gg_result_n_columns(const gg_result *r);
+/* flat view: all columns back to back, offsets[c]..offsets[c+1]              */
+const double *gg_result_flat(const gg_result *r, const uint64_t **offsets);
+void gg_result_free(gg_result *r);
+
+/* ---- column structure, for the bit-identical-structure parity test.  Mirrors
+ *      Column::Column (src/column.cpp:10-39) and
+ *      Column::get_backward_compatible_bipartitions (src/column.cpp:72-122).
+ *      Host only; needs no device.  For column c:
+ *        active  = ids of reads spanning c (ColumnIterator::get_next, src/columniterator.cpp:93-141)
+ *        untagged= subset without haplotag, bit i of the bipartition index is untagged[i]
+ *        shared_mask_prev = bits of column c-1's index whose read is still active at c
+ *      The caller owns nothing: pointers stay valid until gg_plan_free. */
+typedef struct gg_plan gg_plan;
+int gg_plan_build(const gg_problem *p, gg_plan **out, char *err, size_t errlen);
+uint32_t gg_plan_n_columns(const gg_plan *pl);
+const uint32_t *gg_plan_active(const gg_plan *pl, uint32_t column, uint32_t *n);
+const uint32_t *gg_plan_untagged(const gg_plan *pl, uint32_t column, uint32_t *n);
+uint32_t gg_plan_shared_mask_prev(const gg_plan *pl, uint32_t column, uint32_t *n_shared);
+/* all bipartition indices of column c-1 compatible with index b of column c, ascending */
+uint32_t gg_plan_compatible_prev(const gg_plan *pl, uint32_t column, uint32_t b,
+                                 uint32_t *out, uint32_t out_cap);
+void gg_plan_free(gg_plan *pl);
+
+/* ---- host helpers that define the kernel's inputs bit-for-bit ---- */
+/* Entry::set_emission_score (src/entry.cpp:50-64): p_i = 10^-reg + 1/sum_j base^(e_j-e_i), normalised. */
+void gg_entry_emission(const double *scores, uint32_t n, int32_t reg_const, double base_const, double *out);
+/* TransitionProbabilityComputer (src/transitionprobabilitycomputer.cpp:10-15). */
+void gg_transition_scalars(float recombcost, uint32_t n_haps, double *pr, double *qr);
+/* binomial_coefficient (src/binomial.cpp:5-15). */
+int32_t gg_binomial_coefficient(int32_t n, int32_t k);
+
+/* ---- derived calls: determine_genotype (giggles/cli/genotype.py:82-95)
+ *      and GQ / GL (giggles/vcf.py:850-872) for all columns of a result, in C.
+ *      gt_index[c] = genotype index or -1 for "./.", gq[c] integer quality or -1
+ *      when undefined, gl_log10 flat like gg_result_flat (floored at -1000). */
+int gg_result_call(const gg_result *r, double gt_qual_threshold, int32_t *gt_index,
+                   int32_t *gq, double *gl_log10);
+
+const char *gg_version(void);
+int gg_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIGGLES_B200_H */
