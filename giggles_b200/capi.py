@@ -1,0 +1,320 @@
+"""ctypes binding of the C ABI (include/giggles_b200.h) -> libgiggles_b200.so.
+
+This is the reference-side stub a maintainer would write in Python; the Cython
+surface (giggles_b200/core.pyx) binds the same entry points from C++.  There is
+no fallback: if the shared library is missing, importing :func:`lib` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from .problem import Problem, as_ptr
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgiggles_b200.so")
+
+GG_OK, GG_ERR_INVALID, GG_ERR_NO_DEVICE, GG_ERR_CUDA, GG_ERR_NOMEM, GG_ERR_UNSUPPORTED = range(6)
+GG_MAX_ALLELES = 16
+GG_MAX_UNTAGGED = 24
+
+
+class GGError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(message)
+        self.status = status
+
+
+class gg_problem(C.Structure):
+    _fields_ = [
+        ("n_columns", C.c_uint32),
+        ("n_haps", C.c_uint32),
+        ("positions", C.POINTER(C.c_uint32)),
+        ("n_alleles", C.POINTER(C.c_uint32)),
+        ("allele_ref", C.POINTER(C.c_int32)),
+        ("recomb", C.POINTER(C.c_float)),
+        ("n_reads", C.c_uint32),
+        ("read_tag", C.POINTER(C.c_int8)),
+        ("read_entry_offset", C.POINTER(C.c_uint32)),
+        ("entry_column", C.POINTER(C.c_uint32)),
+        ("entry_allele", C.POINTER(C.c_int32)),
+        ("entry_em_offset", C.POINTER(C.c_uint64)),
+        ("entry_em", C.POINTER(C.c_double)),
+    ]
+
+
+class gg_options(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32),
+        ("state_budget_bytes", C.c_uint64),
+        ("precision", C.c_int32),
+        ("kernel_variant", C.c_int32),
+    ]
+
+
+class gg_stats(C.Structure):
+    _fields_ = [
+        ("n_columns", C.c_uint64),
+        ("state_columns", C.c_uint64),
+        ("algorithmic_bytes", C.c_uint64),
+        ("scheduled_bytes", C.c_uint64),
+        ("n_launches", C.c_uint64),
+        ("n_backward_steps", C.c_uint64),
+        ("n_forward_steps", C.c_uint64),
+        ("state_bytes_reserved", C.c_uint64),
+        ("max_untagged", C.c_uint32),
+        ("checkpoint_levels", C.c_uint32),
+        ("last_sweep_ms", C.c_float),
+        ("last_fwdbwd_kernel_ms", C.c_float),
+        ("last_fwd_ms", C.c_float),
+        ("last_bwd_ms", C.c_float),
+        ("last_emit_ms", C.c_float),
+        ("reserved", C.c_float),
+    ]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+# every symbol include/giggles_b200.h declares (tests check that the library exports them all)
+SYMBOLS = [
+    "gg_hmm_run", "gg_hmm_create", "gg_hmm_sweep", "gg_hmm_fetch", "gg_hmm_stats", "gg_hmm_destroy",
+    "gg_result_likelihoods", "gg_result_n_columns", "gg_result_flat", "gg_result_free", "gg_result_call", "gg_result_from_host",
+    "gg_plan_build", "gg_plan_n_columns", "gg_plan_active", "gg_plan_untagged", "gg_plan_shared_mask_prev",
+    "gg_plan_compatible_prev", "gg_plan_free",
+    "gg_entry_emission", "gg_entry_emission_batch", "gg_transition_scalars", "gg_binomial_coefficient",
+    "gg_schedule_dry_run", "gg_version", "gg_device_count",
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libgiggles_b200.so (built by ``__graft_entry__.build()`` / ``make -C giggles_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C giggles_b200/csrc` "
+            "(there is no CPU or PyTorch fallback for the GenotypeHMM path)")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32, dbl = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32, C.c_double
+    errargs = [C.c_char_p, C.c_size_t]
+    L.gg_hmm_run.argtypes = [C.POINTER(gg_problem), C.POINTER(gg_options), C.POINTER(vp)] + errargs
+    L.gg_hmm_create.argtypes = [C.POINTER(gg_problem), C.POINTER(gg_options), C.POINTER(vp)] + errargs
+    L.gg_hmm_sweep.argtypes = [vp, C.c_int] + errargs
+    L.gg_hmm_fetch.argtypes = [vp, C.POINTER(vp)] + errargs
+    L.gg_hmm_stats.argtypes = [vp, C.POINTER(gg_stats)]
+    L.gg_hmm_destroy.argtypes = [vp]
+    L.gg_hmm_destroy.restype = None
+    L.gg_result_likelihoods.argtypes = [vp, u32, C.POINTER(u32)]
+    L.gg_result_likelihoods.restype = C.POINTER(dbl)
+    L.gg_result_n_columns.argtypes = [vp]
+    L.gg_result_n_columns.restype = u32
+    L.gg_result_flat.argtypes = [vp, C.POINTER(C.POINTER(u64))]
+    L.gg_result_flat.restype = C.POINTER(dbl)
+    L.gg_result_free.argtypes = [vp]
+    L.gg_result_free.restype = None
+    L.gg_result_call.argtypes = [vp, dbl, C.POINTER(i32), C.POINTER(i32), C.POINTER(dbl)]
+    L.gg_plan_build.argtypes = [C.POINTER(gg_problem), C.POINTER(vp)] + errargs
+    L.gg_plan_n_columns.argtypes = [vp]
+    L.gg_plan_n_columns.restype = u32
+    L.gg_plan_active.argtypes = [vp, u32, C.POINTER(u32)]
+    L.gg_plan_active.restype = C.POINTER(u32)
+    L.gg_plan_untagged.argtypes = [vp, u32, C.POINTER(u32)]
+    L.gg_plan_untagged.restype = C.POINTER(u32)
+    L.gg_plan_shared_mask_prev.argtypes = [vp, u32, C.POINTER(u32)]
+    L.gg_plan_shared_mask_prev.restype = u32
+    L.gg_plan_compatible_prev.argtypes = [vp, u32, u32, C.POINTER(u32), u32]
+    L.gg_plan_compatible_prev.restype = u32
+    L.gg_plan_free.argtypes = [vp]
+    L.gg_plan_free.restype = None
+    L.gg_entry_emission.argtypes = [C.POINTER(dbl), u32, i32, dbl, C.POINTER(dbl)]
+    L.gg_entry_emission.restype = None
+    L.gg_entry_emission_batch.argtypes = [C.POINTER(dbl), C.POINTER(u64), u64, i32, dbl, C.POINTER(dbl)]
+    L.gg_entry_emission_batch.restype = None
+    L.gg_transition_scalars.argtypes = [C.c_float, u32, C.POINTER(dbl), C.POINTER(dbl)]
+    L.gg_transition_scalars.restype = None
+    L.gg_binomial_coefficient.argtypes = [i32, i32]
+    L.gg_binomial_coefficient.restype = i32
+    L.gg_schedule_dry_run.argtypes = [u32, C.POINTER(u64), C.POINTER(u64), u64, C.POINTER(u64), C.POINTER(u32),
+                                      C.POINTER(u64), C.POINTER(u64)] + errargs
+    L.gg_version.restype = C.c_char_p
+    L.gg_device_count.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _check(rc: int, err) -> None:
+    if rc != GG_OK:
+        raise GGError(rc, err.value.decode(errors="replace") or f"gg error {rc}")
+
+
+def entry_emission(scores, reg_const: int = 10, base_const: float = float(np.e)) -> np.ndarray:
+    """Entry::set_emission_score (reference src/entry.cpp:50-64)."""
+    s = np.ascontiguousarray(scores, dtype=np.float64)
+    out = np.empty_like(s)
+    lib().gg_entry_emission(as_ptr(s, C.c_double), s.size, int(reg_const), float(base_const), as_ptr(out, C.c_double))
+    return out
+
+
+def transition_scalars(recombcost: float, n_haps: int):
+    pr, qr = C.c_double(), C.c_double()
+    lib().gg_transition_scalars(C.c_float(recombcost), n_haps, C.byref(pr), C.byref(qr))
+    return pr.value, qr.value
+
+
+class CProblem:
+    """A :class:`Problem` laid out as ``gg_problem``: raw scores are turned into the normalised
+    emission probabilities of ``Entry::set_emission_score`` by ``gg_entry_emission``."""
+
+    def __init__(self, p: Problem):
+        self.p = p
+        L = lib()
+        em = np.empty_like(p.entry_scores)
+        L.gg_entry_emission_batch(as_ptr(p.entry_scores, C.c_double), as_ptr(p.entry_score_offset, C.c_uint64),
+                                  p.n_entries, p.reg_const, p.base_const, as_ptr(em, C.c_double))
+        self.entry_em = em
+        self.struct = gg_problem(
+            p.n_columns, p.n_haps,
+            as_ptr(p.positions, C.c_uint32), as_ptr(p.n_alleles, C.c_uint32), as_ptr(p.allele_ref, C.c_int32),
+            as_ptr(p.recomb, C.c_float), p.n_reads, as_ptr(p.read_tag, C.c_int8),
+            as_ptr(p.read_entry_offset, C.c_uint32), as_ptr(p.entry_column, C.c_uint32),
+            as_ptr(p.entry_allele, C.c_int32), as_ptr(p.entry_score_offset, C.c_uint64), as_ptr(em, C.c_double))
+
+
+@dataclass
+class Calls:
+    gt_index: np.ndarray   # int32 [C], -1 = no call
+    gq: np.ndarray         # int32 [C], -1 = undefined
+    gl_log10: np.ndarray   # float64 flat
+
+
+class Result:
+    def __init__(self, handle):
+        self._h = handle
+        L = lib()
+        offs = C.POINTER(C.c_uint64)()
+        flat = L.gg_result_flat(handle, C.byref(offs))
+        n = L.gg_result_n_columns(handle)
+        self.offsets = np.ctypeslib.as_array(offs, shape=(n + 1,)).copy() if n else np.zeros(1, np.uint64)
+        total = int(self.offsets[-1])
+        self.values = np.ctypeslib.as_array(flat, shape=(total,)).copy() if total else np.zeros(0)
+
+    def column(self, c: int) -> np.ndarray:
+        return self.values[int(self.offsets[c]):int(self.offsets[c + 1])]
+
+    def call(self, gt_qual_threshold: float = 0.0) -> Calls:
+        n = len(self.offsets) - 1
+        gt = np.empty(n, np.int32)
+        gq = np.empty(n, np.int32)
+        gl = np.empty(self.values.shape[0], np.float64)
+        lib().gg_result_call(self._h, float(gt_qual_threshold), as_ptr(gt, C.c_int32), as_ptr(gq, C.c_int32),
+                             as_ptr(gl, C.c_double))
+        return Calls(gt, gq, gl)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().gg_result_free(self._h)
+            self._h = None
+
+
+def _options(device=-1, budget=0, precision=0, kernel_variant=0):
+    return gg_options(int(device), int(budget), int(precision), int(kernel_variant))
+
+
+def hmm_run(p: Problem | CProblem, device: int = -1, budget: int = 0, precision: int = 0,
+            kernel_variant: int = 0) -> Result:
+    """``gg_hmm_run``: host buffers in, host posteriors out (what ``new GenotypeHMM(...)`` does in the reference)."""
+    cp = p if isinstance(p, CProblem) else CProblem(p)
+    err = C.create_string_buffer(512)
+    out = C.c_void_p()
+    o = _options(device, budget, precision, kernel_variant)
+    _check(lib().gg_hmm_run(C.byref(cp.struct), C.byref(o), C.byref(out), err, len(err)), err)
+    return Result(out)
+
+
+class Hmm:
+    """Staged form: ``create`` (plan + H2D), ``sweep`` (device only), ``fetch`` (D2H)."""
+
+    def __init__(self, p: Problem | CProblem, device: int = -1, budget: int = 0, precision: int = 0,
+                 kernel_variant: int = 0):
+        self.cp = p if isinstance(p, CProblem) else CProblem(p)
+        err = C.create_string_buffer(512)
+        self._h = C.c_void_p()
+        o = _options(device, budget, precision, kernel_variant)
+        _check(lib().gg_hmm_create(C.byref(self.cp.struct), C.byref(o), C.byref(self._h), err, len(err)), err)
+
+    def sweep(self, timed_kernels: bool = False) -> None:
+        err = C.create_string_buffer(512)
+        _check(lib().gg_hmm_sweep(self._h, int(timed_kernels), err, len(err)), err)
+
+    def fetch(self) -> Result:
+        err = C.create_string_buffer(512)
+        out = C.c_void_p()
+        _check(lib().gg_hmm_fetch(self._h, C.byref(out), err, len(err)), err)
+        return Result(out)
+
+    def stats(self) -> dict:
+        s = gg_stats()
+        lib().gg_hmm_stats(self._h, C.byref(s))
+        return s.as_dict()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().gg_hmm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class PlanView:
+    """Column structure as the product derives it (``gg_plan_*``), for the structure parity test."""
+
+    def __init__(self, p: Problem | CProblem):
+        self.cp = p if isinstance(p, CProblem) else CProblem(p)
+        err = C.create_string_buffer(512)
+        self._h = C.c_void_p()
+        _check(lib().gg_plan_build(C.byref(self.cp.struct), C.byref(self._h), err, len(err)), err)
+        self.n_columns = lib().gg_plan_n_columns(self._h)
+
+    def _ids(self, fn, c):
+        n = C.c_uint32()
+        ptr = fn(self._h, c, C.byref(n))
+        return [ptr[i] for i in range(n.value)]
+
+    def active(self, c):
+        return self._ids(lib().gg_plan_active, c)
+
+    def untagged(self, c):
+        return self._ids(lib().gg_plan_untagged, c)
+
+    def shared_mask_prev(self, c):
+        n = C.c_uint32()
+        m = lib().gg_plan_shared_mask_prev(self._h, c, C.byref(n))
+        return m, n.value
+
+    def compatible_prev(self, c, b, cap=1 << 16):
+        buf = (C.c_uint32 * cap)()
+        n = lib().gg_plan_compatible_prev(self._h, c, b, buf, cap)
+        return [buf[i] for i in range(min(n, cap))]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().gg_plan_free(self._h)
+            self._h = None
+
+
+def schedule_dry_run(col_bytes, fg_bytes, budget):
+    cb = np.ascontiguousarray(col_bytes, dtype=np.uint64)
+    fb = np.ascontiguousarray(fg_bytes, dtype=np.uint64)
+    arena, levels, nb, nf = C.c_uint64(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+    err = C.create_string_buffer(512)
+    rc = lib().gg_schedule_dry_run(cb.size, as_ptr(cb, C.c_uint64), as_ptr(fb, C.c_uint64), int(budget),
+                                   C.byref(arena), C.byref(levels), C.byref(nb), C.byref(nf), err, len(err))
+    _check(rc, err)
+    return dict(arena_bytes=arena.value, levels=levels.value, n_bwd=nb.value, n_fwd=nf.value)

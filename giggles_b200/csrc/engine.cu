@@ -1,0 +1,562 @@
+// Device engine + compute half of the C ABI (include/giggles_b200.h).
+//
+// gg_hmm_create  = plan on the host (plan.cpp), checkpoint schedule (schedule.cpp), H2D of the tables
+// gg_hmm_sweep   = replay the schedule: emission tables, backward steps, forward steps (+ posterior)
+// gg_hmm_fetch   = D2H of the genotype tables
+// There is no CPU path: without a CUDA device every entry point fails with GG_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/giggles_b200.h"
+#include "hmm_kernels.cuh"
+#include "hmm_tma_kernel.cuh"
+#include "plan.hpp"
+#include "result.hpp"
+#include "schedule.hpp"
+
+namespace gg {
+
+struct CudaError : std::runtime_error {
+    int status;
+    CudaError(int st, const std::string &m) : std::runtime_error(m), status(st) {}
+};
+
+#define GG_CUDA(call)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess) {                                                                             \
+            int st__ = (e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver) ? GG_ERR_NO_DEVICE    \
+                       : (e__ == cudaErrorMemoryAllocation ? GG_ERR_NOMEM : GG_ERR_CUDA);                     \
+            throw CudaError(st__, std::string(#call) + ": " + cudaGetErrorString(e__));                       \
+        }                                                                                                     \
+    } while (0)
+
+template <typename U>
+struct DevBuf {
+    U *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) GG_CUDA(cudaMalloc(&p, count * sizeof(U)));
+    }
+    void upload(const std::vector<U> &h, cudaStream_t st) {
+        alloc(h.size());
+        if (!h.empty()) GG_CUDA(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(U), cudaMemcpyHostToDevice, st));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+struct LaunchShape {
+    int V, NS;
+    uint32_t G, nwarps_fwd, nwarps_bwd;
+};
+
+}  // namespace gg
+
+using namespace gg;
+
+struct gg_hmm {
+    Plan plan;
+    Schedule sched;
+    bool fp64 = false;
+    int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only
+    int device = 0;
+    int num_sms = 0;
+    size_t elem = 4;
+    cudaStream_t stream = nullptr;
+    std::vector<uint64_t> colb, fgb, fg_prefix_elems;
+    DevBuf<ColDesc> d_cols;
+    DevBuf<uint8_t> d_em_side, d_allele1;
+    DevBuf<double> d_em_prob, d_scale_a, d_scale_b, d_result;
+    DevBuf<uint16_t> d_row_order;
+    DevBuf<unsigned char> d_arena, d_partial;
+    DevBuf<unsigned int> d_counter;
+    uint32_t max_grid = 0;
+    LaunchShape shape{};
+    std::map<std::tuple<const void *, int, size_t>, int> occ_cache;
+    gg_stats stats{};
+    std::vector<cudaEvent_t> ev;   // timing events (timed sweeps only)
+    ~gg_hmm() {
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace gg {
+
+static void set_err(char *err, size_t errlen, const std::string &m) {
+    if (err && errlen) {
+        std::strncpy(err, m.c_str(), errlen - 1);
+        err[errlen - 1] = 0;
+    }
+}
+
+static uint32_t pow2ceil(uint32_t x) {
+    uint32_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+template <typename T>
+static LaunchShape choose_shape(uint32_t R) {
+    LaunchShape s{};
+    const int maxV = sizeof(T) == 4 ? 4 : 2;
+    s.V = (maxV >= 4 && R % 4 == 0) ? 4 : (R % 2 == 0 ? 2 : 1);
+    const uint32_t vecs = R / s.V;
+    s.G = std::min<uint32_t>(32, pow2ceil(vecs));
+    uint32_t ns = (vecs + s.G - 1) / s.G;
+    s.NS = (int)pow2ceil(ns);
+    if (s.NS > 8) throw CudaError(GG_ERR_UNSUPPORTED, "n_haps too large for the vector width its parity allows (use a multiple of 4)");
+    const uint32_t rpi = 32 / s.G;
+    s.nwarps_fwd = s.nwarps_bwd = std::min<uint32_t>(8, pow2ceil((R + rpi - 1) / rpi));
+    return s;
+}
+
+template <typename T, int V, int NS>
+static const void *kernel_ptr(bool fwd) {
+    return fwd ? (const void *)step_kernel<T, V, NS, true> : (const void *)step_kernel<T, V, NS, false>;
+}
+
+template <typename T>
+static const void *pick_kernel(int V, int NS, bool fwd) {
+#define GG_PICK(VV, NN) \
+    if (V == VV && NS == NN) return kernel_ptr<T, VV, NN>(fwd);
+    GG_PICK(1, 1) GG_PICK(1, 2) GG_PICK(1, 4) GG_PICK(1, 8)
+    GG_PICK(2, 1) GG_PICK(2, 2) GG_PICK(2, 4) GG_PICK(2, 8)
+    if (sizeof(T) == 4) {
+        if (V == 4 && NS == 1) return kernel_ptr<float, 4, 1>(fwd);
+        if (V == 4 && NS == 2) return kernel_ptr<float, 4, 2>(fwd);
+        if (V == 4 && NS == 4) return kernel_ptr<float, 4, 4>(fwd);
+        if (V == 4 && NS == 8) return kernel_ptr<float, 4, 8>(fwd);
+    }
+#undef GG_PICK
+    throw CudaError(GG_ERR_UNSUPPORTED, "no kernel for this vector shape");
+}
+
+static constexpr size_t kMaxDynSmem = 200 * 1024;
+static constexpr size_t kMaxDynSmemTma = 222 * 1024;   // 227 KB per CTA minus the kernel's static shared memory
+
+template <typename T>
+struct Engine {
+    static uint64_t block_stride(uint32_t R) { return ((uint64_t)R * R + 2 * R + 4 + 3) & ~(uint64_t)3; }
+    static uint64_t col_elems(uint32_t u, uint32_t R) { return block_stride(R) << u; }
+    static uint64_t fg_elems(uint32_t u, uint32_t nA) { return ((uint64_t)2 * (nA + 1)) << u; }
+
+    static void launch_step(gg_hmm *h, const Op &op, bool fwd, bool init) {
+        const Plan &pl = h->plan;
+        const uint32_t R = pl.n_haps;
+        const uint32_t co = op.c;
+        const ColumnPlan &pco = pl.cols[co];
+        unsigned char *arena = h->d_arena.p;
+        StepArgs<T> a{};
+        a.R = R;
+        a.G = h->shape.G;
+        a.BS = (uint32_t)block_stride(R);
+        a.out = reinterpret_cast<T *>(arena + op.out_off);
+        a.fg_out = reinterpret_cast<const T *>(arena + op.fg_out_off);
+        a.u_out = pco.u;
+        a.nA_out = pco.n_alleles;
+        a.al_out = h->d_allele1.p + (size_t)co * R;
+        a.partial = reinterpret_cast<T *>(h->d_partial.p);
+        a.counter = h->d_counter.p;
+        a.result = h->d_result.p + pco.gl_off;
+        a.tA = 1.0; a.tB = 0.0; a.tC = 0.0;
+        if (fwd) {
+            a.beta = reinterpret_cast<const T *>(arena + op.beta_off);
+            a.row_order = h->d_row_order.p + (size_t)co * R;
+            a.out_scale = h->d_scale_a.p + co;
+            if (co > 0) {
+                const ColumnPlan &pci = pl.cols[co - 1];
+                a.in = reinterpret_cast<const T *>(arena + op.in_off);
+                a.in_scale = h->d_scale_a.p + (co - 1);
+                a.al_in = h->d_allele1.p + (size_t)(co - 1) * R;
+                a.u_in = pci.u;
+                a.nA_in = pci.n_alleles;
+                a.n_sh = pco.n_sh;
+                a.shared_mask = pco.shared_mask_prev;
+                a.free_mask = pco.term_mask_prev;
+                a.n_free_left = pco.n_term_prev;
+                a.tA = pco.tA; a.tB = pco.tB; a.tC = pco.tC;
+            } else {
+                a.n_sh = pco.u;   // no bits to broadcast: item index == bipartition index
+                a.al_in = a.al_out;
+            }
+        } else {
+            a.out_scale = h->d_scale_b.p + co;
+            if (!init) {
+                const uint32_t ci = co + 1;
+                const ColumnPlan &pci = pl.cols[ci];
+                a.in = reinterpret_cast<const T *>(arena + op.in_off);
+                a.fg_in = reinterpret_cast<const T *>(arena + op.fg_in_off);
+                a.in_scale = h->d_scale_b.p + ci;
+                a.al_in = h->d_allele1.p + (size_t)ci * R;
+                a.u_in = pci.u;
+                a.nA_in = pci.n_alleles;
+                a.n_sh = pci.n_sh;
+                a.shared_mask = pci.shared_mask_prev;
+                a.free_mask = pci.term_mask_prev;
+                a.n_free_left = pci.n_term_prev;
+                a.tA = pci.tA; a.tB = pci.tB; a.tC = pci.tC;
+            } else {
+                a.n_sh = pco.u;
+                a.shared_mask = pco.u >= 32 ? 0xffffffffu : ((1u << pco.u) - 1u);
+                a.free_mask = 0;
+                a.n_free_left = 0;
+                a.al_in = a.al_out;
+            }
+        }
+        if (try_launch_tma(h, a, pco, fwd)) return;
+        const uint32_t rpi = 32 / h->shape.G;
+        uint32_t nwarps = fwd ? h->shape.nwarps_fwd : h->shape.nwarps_bwd;
+        SmemLayout L = smem_layout<T>(R, nwarps * rpi, pco.n_alleles + 1, fwd);
+        while (L.total > kMaxDynSmem && nwarps > 1) {
+            nwarps >>= 1;
+            L = smem_layout<T>(R, nwarps * rpi, pco.n_alleles + 1, fwd);
+        }
+        if (L.total > kMaxDynSmem) throw CudaError(GG_ERR_UNSUPPORTED, "column needs more shared memory than one SM has");
+        const void *k = pick_kernel<T>(h->shape.V, h->shape.NS, fwd);
+        const int threads = (int)nwarps * 32;
+        auto key = std::make_tuple(k, threads, (size_t)L.total);
+        auto it = h->occ_cache.find(key);
+        int occ;
+        if (it == h->occ_cache.end()) {
+            GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, L.total));
+            if (occ < 1) throw CudaError(GG_ERR_CUDA, "step kernel does not fit on an SM");
+            h->occ_cache[key] = occ;
+        } else {
+            occ = it->second;
+        }
+        const uint64_t n_items = (uint64_t)1 << pco.u;
+        uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)h->num_sms * occ);
+        grid = std::min(grid, h->max_grid);
+        void *params[] = {(void *)&a};
+        GG_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(threads), params, L.total, h->stream));
+        ++h->stats.n_launches;
+    }
+
+    // Pipelined bulk-copy kernel (hmm_tma_kernel.cuh): fp32, R % 4 == 0, one block record per stage.
+    static bool try_launch_tma(gg_hmm *h, const StepArgs<T> &a, const ColumnPlan &pco, bool fwd) {
+        if (sizeof(T) != 4 || h->kernel_variant == 1 || a.in == nullptr) return false;
+        if (a.R % 4 != 0 || a.R > 128 || h->shape.V != 4 || h->shape.NS != 1) return false;
+        const uint32_t rpi = 32 / a.G, ngrp = kTmaConsumerWarps * rpi;
+        const uint32_t nred = fwd ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
+        uint32_t stages = kTmaMaxStages;
+        TmaSmemLayout L = tma_smem_layout(a.R, a.BS, stages, ngrp, pco.n_alleles + 1, fwd, nred > 1);
+        while (L.total > kMaxDynSmemTma && stages > 3) {
+            --stages;
+            L = tma_smem_layout(a.R, a.BS, stages, ngrp, pco.n_alleles + 1, fwd, nred > 1);
+        }
+        if (L.total > kMaxDynSmemTma) return false;
+        const void *k = fwd ? (const void *)step_tma_kernel<true> : (const void *)step_tma_kernel<false>;
+        static bool attr_done = false;
+        if (!attr_done) {
+            GG_CUDA(cudaFuncSetAttribute((const void *)step_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
+            GG_CUDA(cudaFuncSetAttribute((const void *)step_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
+            attr_done = true;
+        }
+        const uint64_t n_items = (uint64_t)1 << pco.u;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)h->num_sms);
+        StepArgs<float> af;
+        static_assert(sizeof(af) == sizeof(StepArgs<T>) || sizeof(T) != 4, "layout");
+        std::memcpy(&af, &a, sizeof(af));
+        uint32_t ns = stages;
+        void *params[] = {(void *)&af, (void *)&ns};
+        GG_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(kTmaThreads), params, L.total, h->stream));
+        ++h->stats.n_launches;
+        return true;
+    }
+
+    static void launch_emit(gg_hmm *h, const Op &op) {
+        const Plan &pl = h->plan;
+        uint32_t lo = op.c;
+        T *region = reinterpret_cast<T *>(h->d_arena.p + op.out_off);
+        const uint64_t prefix_lo = h->fg_prefix_elems[op.c];
+        while (lo <= op.hi) {
+            const uint32_t n = std::min<uint32_t>(op.hi - lo + 1, 32768);
+            uint32_t umax = 0;
+            for (uint32_t c = lo; c < lo + n; ++c) umax = std::max(umax, pl.cols[c].u);
+            const uint64_t work = fg_elems(umax, pl.max_alleles);
+            const uint32_t bx = (uint32_t)std::min<uint64_t>((work + 255) / 256, 2048);
+            emission_kernel<T><<<dim3(bx, n), 256, 0, h->stream>>>(h->d_cols.p, h->d_em_side.p, h->d_em_prob.p, region,
+                                                                   prefix_lo, lo);
+            GG_CUDA(cudaGetLastError());
+            ++h->stats.n_launches;
+            lo += n;
+        }
+    }
+
+    static void set_attrs() {
+        static bool done = false;   // per process and per T
+        if (done) return;
+        for (int V : {1, 2, 4})
+            for (int NS : {1, 2, 4, 8})
+                for (bool fwd : {false, true}) {
+                    if (V == 4 && sizeof(T) != 4) continue;
+                    const void *k = pick_kernel<T>(V, NS, fwd);
+                    GG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+                }
+        done = true;
+    }
+
+    static void create(gg_hmm *h, const gg_options *o) {
+        Plan &pl = h->plan;
+        const uint32_t C = pl.n_columns, R = pl.n_haps;
+        h->elem = sizeof(T);
+        h->shape = choose_shape<T>(R);
+        set_attrs();
+        h->colb.resize(C);
+        h->fgb.resize(C);
+        h->fg_prefix_elems.assign(C + 1, 0);
+        std::vector<ColDesc> cd(C);
+        for (uint32_t c = 0; c < C; ++c) {
+            const ColumnPlan &cp = pl.cols[c];
+            h->colb[c] = col_elems(cp.u, R) * sizeof(T);
+            h->fgb[c] = fg_elems(cp.u, cp.n_alleles) * sizeof(T);
+            h->fg_prefix_elems[c + 1] = h->fg_prefix_elems[c] + fg_elems(cp.u, cp.n_alleles);
+            cd[c].u = cp.u;
+            cd[c].n_alleles = cp.n_alleles;
+            cd[c].em_count = cp.em_count;
+            cd[c].em_off = cp.em_off;
+            cd[c].em_prob_off = cp.em_prob_off;
+            cd[c].fg_prefix = h->fg_prefix_elems[c];
+        }
+        // static tables first, then size the arena from what is left
+        h->d_cols.upload(cd, h->stream);
+        h->d_em_side.upload(pl.em_side, h->stream);
+        h->d_em_prob.upload(pl.em_prob, h->stream);
+        h->d_allele1.upload(pl.allele1, h->stream);
+        h->d_row_order.upload(pl.row_order, h->stream);
+        h->d_scale_a.alloc(C);
+        h->d_scale_b.alloc(C);
+        h->d_result.alloc(pl.gl_offsets[C]);
+        h->d_counter.alloc(1);
+        GG_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned int), h->stream));
+        h->max_grid = (uint32_t)h->num_sms * 16;
+        h->d_partial.alloc((size_t)h->max_grid * kPartialStride * sizeof(T));
+        uint64_t budget = o ? o->state_budget_bytes : 0;
+        if (budget == 0) {
+            size_t free_b = 0, total_b = 0;
+            GG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            budget = (uint64_t)(free_b * 0.8);
+        }
+        // if everything fits there is no reason to reserve more than that
+        uint64_t all = 0;
+        for (uint32_t c = 0; c < C; ++c) all += h->colb[c] + h->fgb[c] + 512;
+        uint64_t maxcol = 0;
+        for (uint32_t c = 0; c < C; ++c) maxcol = std::max(maxcol, h->colb[c]);
+        budget = std::min<uint64_t>(budget, all + 3 * maxcol + 4096);
+        try {
+            build_schedule(h->colb, h->fgb, budget, h->sched);
+            validate_schedule(h->colb, h->fgb, h->sched);
+        } catch (const CudaError &) {
+            throw;
+        } catch (const std::runtime_error &e) {
+            const std::string m = e.what();
+            throw CudaError(m.find("budget") != std::string::npos ? GG_ERR_NOMEM : GG_ERR_INVALID, m);
+        }
+        h->d_arena.alloc(h->sched.arena_bytes);
+        GG_CUDA(cudaStreamSynchronize(h->stream));
+        // stats that do not depend on a sweep
+        gg_stats &st = h->stats;
+        st.n_columns = C;
+        st.state_columns = pl.state_columns;
+        st.algorithmic_bytes = 5 * (uint64_t)sizeof(T) * pl.state_columns;
+        st.state_bytes_reserved = h->sched.arena_bytes;
+        st.max_untagged = pl.max_u;
+        st.checkpoint_levels = h->sched.levels;
+        st.n_backward_steps = h->sched.n_bwd;
+        st.n_forward_steps = h->sched.n_fwd;
+        uint64_t sb = 0;
+        auto S = [&](uint32_t c) { return ((uint64_t)R * R) << pl.cols[c].u; };
+        for (const Op &op : h->sched.ops) {
+            if (op.kind == OP_FWD) sb += (2 * S(op.c) + (op.c > 0 ? S(op.c - 1) : 0)) * sizeof(T);
+            else if (op.kind == OP_BWD) sb += (S(op.c) + S(op.c + 1)) * sizeof(T);
+            else if (op.kind == OP_BWD_INIT) sb += S(op.c) * sizeof(T);
+        }
+        st.scheduled_bytes = sb;
+    }
+
+    static void sweep(gg_hmm *h, int timed) {
+        gg_stats &st = h->stats;
+        st.n_launches = 0;
+        const size_t nops = h->sched.ops.size();
+        const bool per_kernel = timed != 0;
+        if (h->ev.size() < 2) {
+            h->ev.resize(2);
+            GG_CUDA(cudaEventCreate(&h->ev[0]));
+            GG_CUDA(cudaEventCreate(&h->ev[1]));
+        }
+        if (per_kernel && h->ev.size() < 2 + 2 * nops) {
+            size_t old = h->ev.size();
+            h->ev.resize(2 + 2 * nops);
+            for (size_t i = old; i < h->ev.size(); ++i) GG_CUDA(cudaEventCreate(&h->ev[i]));
+        }
+        GG_CUDA(cudaEventRecord(h->ev[0], h->stream));
+        for (size_t i = 0; i < nops; ++i) {
+            const Op &op = h->sched.ops[i];
+            if (per_kernel) GG_CUDA(cudaEventRecord(h->ev[2 + 2 * i], h->stream));
+            switch (op.kind) {
+            case OP_EMIT: launch_emit(h, op); break;
+            case OP_BWD_INIT: launch_step(h, op, false, true); break;
+            case OP_BWD: launch_step(h, op, false, false); break;
+            case OP_FWD: launch_step(h, op, true, false); break;
+            }
+            if (per_kernel) GG_CUDA(cudaEventRecord(h->ev[3 + 2 * i], h->stream));
+        }
+        GG_CUDA(cudaEventRecord(h->ev[1], h->stream));
+        GG_CUDA(cudaStreamSynchronize(h->stream));
+        GG_CUDA(cudaEventElapsedTime(&st.last_sweep_ms, h->ev[0], h->ev[1]));
+        st.last_fwdbwd_kernel_ms = 0.f;
+        st.last_fwd_ms = st.last_bwd_ms = st.last_emit_ms = 0.f;
+        if (per_kernel) {
+            for (size_t i = 0; i < nops; ++i) {
+                float ms = 0.f;
+                GG_CUDA(cudaEventElapsedTime(&ms, h->ev[2 + 2 * i], h->ev[3 + 2 * i]));
+                switch (h->sched.ops[i].kind) {
+                case OP_EMIT: st.last_emit_ms += ms; break;
+                case OP_FWD: st.last_fwd_ms += ms; break;
+                default: st.last_bwd_ms += ms; break;
+                }
+            }
+            st.last_fwdbwd_kernel_ms = st.last_fwd_ms + st.last_bwd_ms;
+        }
+    }
+};
+
+}  // namespace gg
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+template <typename F>
+static int guarded(char *err, size_t errlen, F &&f) {
+    try {
+        f();
+        return GG_OK;
+    } catch (const CudaError &e) {
+        set_err(err, errlen, e.what());
+        return e.status;
+    } catch (const std::bad_alloc &) {
+        set_err(err, errlen, "out of host memory");
+        return GG_ERR_NOMEM;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, e.what());
+        return GG_ERR_INVALID;
+    }
+}
+
+extern "C" {
+
+int gg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int gg_hmm_create(const gg_problem *p, const gg_options *o, gg_hmm **out, char *err, size_t errlen) {
+    if (out) *out = nullptr;
+    gg_hmm *h = nullptr;
+    int rc = guarded(err, errlen, [&] {
+        if (!p || !out) throw std::runtime_error("gg_hmm_create: null argument");
+        h = new gg_hmm();
+        build_plan(*p, h->plan);     // validates the problem before any device work
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            throw CudaError(GG_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+        }
+        int dev = o ? o->device : -1;
+        if (dev >= 0) GG_CUDA(cudaSetDevice(dev));
+        GG_CUDA(cudaGetDevice(&h->device));
+        GG_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+        GG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->fp64 = o && o->precision == 1;
+        h->kernel_variant = o ? o->kernel_variant : 0;
+        if (h->fp64) Engine<double>::create(h, o);
+        else Engine<float>::create(h, o);
+    });
+    if (rc != GG_OK) {
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return GG_OK;
+}
+
+int gg_hmm_sweep(gg_hmm *h, int timed_kernels, char *err, size_t errlen) {
+    return guarded(err, errlen, [&] {
+        if (!h) throw std::runtime_error("gg_hmm_sweep: null handle");
+        GG_CUDA(cudaSetDevice(h->device));
+        if (h->plan.n_columns == 0) return;
+        if (h->fp64) Engine<double>::sweep(h, timed_kernels);
+        else Engine<float>::sweep(h, timed_kernels);
+    });
+}
+
+int gg_hmm_fetch(gg_hmm *h, gg_result **out, char *err, size_t errlen) {
+    if (out) *out = nullptr;
+    return guarded(err, errlen, [&] {
+        if (!h || !out) throw std::runtime_error("gg_hmm_fetch: null argument");
+        GG_CUDA(cudaSetDevice(h->device));
+        gg_result *r = new gg_result();
+        r->offsets = h->plan.gl_offsets;
+        r->values.resize(h->plan.gl_offsets.empty() ? 0 : h->plan.gl_offsets.back());
+        if (!r->values.empty()) {
+            cudaError_t e = cudaMemcpyAsync(r->values.data(), h->d_result.p, r->values.size() * sizeof(double),
+                                            cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) {
+                delete r;
+                throw CudaError(GG_ERR_CUDA, std::string("D2H of the genotype tables: ") + cudaGetErrorString(e));
+            }
+        }
+        *out = r;
+    });
+}
+
+int gg_hmm_stats(const gg_hmm *h, gg_stats *s) {
+    if (!h || !s) return GG_ERR_INVALID;
+    *s = h->stats;
+    return GG_OK;
+}
+
+void gg_hmm_destroy(gg_hmm *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    delete h;
+}
+
+int gg_hmm_run(const gg_problem *p, const gg_options *o, gg_result **out, char *err, size_t errlen) {
+    if (out) *out = nullptr;
+    gg_hmm *h = nullptr;
+    int rc = gg_hmm_create(p, o, &h, err, errlen);
+    if (rc != GG_OK) return rc;
+    rc = gg_hmm_sweep(h, 0, err, errlen);
+    if (rc == GG_OK) rc = gg_hmm_fetch(h, out, err, errlen);
+    gg_hmm_destroy(h);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,423 @@
+// Pipelined column step for sm_100a: bulk-async (TMA) staging of bipartition blocks.
+//
+// Same arithmetic as step_kernel (hmm_kernels.cuh) for fp32 columns with R % 4 == 0 whose block
+// record (R^2 + 2R + 4 floats) fits a shared-memory stage.  One persistent CTA per SM:
+//
+//   warp 0      producer.  For every work item (one output bipartition block) it issues, per input
+//               block, ONE cp.async.bulk global->shared of the whole record (values + row/col/total
+//               sums) into the next free stage of a ring and, for the forward step, one more for the
+//               beta block of the posterior; the copy completes on the stage's "full" mbarrier.  It
+//               also fetches the item's F/G emission vectors into the stage's metadata.
+//   warps 1..8  consumers.  Wait on "full", run the row loop out of shared memory (LDS.128),
+//               store the produced block straight from registers (STG.128), hand the stage back
+//               through its "empty" mbarrier.
+//
+// With n stages of ~31 KB (R = 88) an SM keeps 4-6 records in flight, which is what hides HBM
+// latency; the generic kernel can only keep what its registers hold.
+#pragma once
+#include "hmm_kernels.cuh"
+
+namespace gg {
+
+constexpr int kTmaMaxStages = 8;
+constexpr int kTmaConsumerWarps = 8;
+constexpr int kTmaThreads = 32 * (1 + kTmaConsumerWarps);
+
+struct TmaStageMeta {
+    uint32_t b_out, b_self, pad0, pad1;
+    float fg_out[2 * kMaxClasses + 2];    // F then G of the output block (k == 0 stage only)
+    float fg_self[2 * kMaxClasses + 2];   // backward: F then G of the block held by this stage
+};
+
+struct TmaSmemLayout {
+    uint32_t off_stage, off_meta, off_acc, off_colred, off_totred, off_fgo, off_q, off_al_o, off_al_i, off_rord, total;
+};
+__host__ __device__ inline TmaSmemLayout tma_smem_layout(uint32_t R, uint32_t BS, uint32_t n_stages, uint32_t ngrp,
+                                                         uint32_t ncls_out, bool fwd, bool need_acc) {
+    TmaSmemLayout L;
+    const uint32_t Rp = (R + 3u) & ~3u;
+    const uint32_t stage_bytes = (BS * 4u + 127u) & ~127u;
+    uint32_t o = 0;
+    L.off_stage = o; o += n_stages * stage_bytes;
+    L.off_meta = o; o += n_stages * (uint32_t)sizeof(TmaStageMeta);
+    o = (o + 15u) & ~15u;
+    L.off_acc = o; o += need_acc ? stage_bytes : 0;
+    L.off_colred = o; o += 2 * ngrp * Rp * 4;          // double-buffered across items
+    L.off_totred = o; o += 2 * ngrp * 4;
+    L.off_fgo = o; o += 48 * 4;                          // item's F/G vector when stage 0 is released early
+    L.off_q = o; o += fwd ? ngrp * ncls_out * Rp * 4 : 0;
+    L.off_al_o = o; o += Rp;
+    L.off_al_i = o; o += Rp;
+    o = (o + 3u) & ~3u;
+    L.off_rord = o; o += Rp * 2;
+    L.total = (o + 127u) & ~127u;
+    return L;
+}
+
+// ---- mbarrier / bulk-copy PTX ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kTmaConsumerWarps) : "memory"); }
+
+template <bool FWD>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_full[kTmaMaxStages];
+    __shared__ __align__(8) uint64_t s_empty[kTmaMaxStages];
+    __shared__ double s_W[kPartialStride];
+    __shared__ double s_L[GG_MAX_ALLELES * (GG_MAX_ALLELES + 1) / 2];
+    __shared__ bool s_last;
+
+    const uint32_t R = a.R, G = a.G, BS = a.BS;
+    const uint32_t RR = R * R;
+    const uint32_t Rp = (R + 3u) & ~3u;
+    const uint32_t stage_bytes = (BS * 4u + 127u) & ~127u;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t rpi = 32u / G;
+    const uint32_t ngrp = kTmaConsumerWarps * rpi;
+    const uint32_t NCo = a.nA_out + 1, NCi = a.nA_in + 1;
+    const uint32_t fgs_o = 2 * NCo, fgs_i = 2 * NCi;
+    const uint32_t nred = FWD ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
+    const uint32_t n_bcast = FWD ? (a.u_out - a.n_sh) : a.n_free_left;
+    const uint32_t nload = nred + (FWD ? 1u : 0u);
+    const TmaSmemLayout L = tma_smem_layout(R, BS, n_stages, ngrp, NCo, FWD, nred > 1);
+    TmaStageMeta *s_meta = reinterpret_cast<TmaStageMeta *>(smem_raw + L.off_meta);
+    const uint32_t n_items = 1u << a.u_out;
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < n_stages; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], kTmaConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // consumer-side tables
+    uint8_t *s_al_o = smem_raw + L.off_al_o;
+    uint8_t *s_al_i = smem_raw + L.off_al_i;
+    uint16_t *s_rord = reinterpret_cast<uint16_t *>(smem_raw + L.off_rord);
+    float *s_q = reinterpret_cast<float *>(smem_raw + L.off_q);
+    for (uint32_t t = tid; t < R; t += blockDim.x) {
+        s_al_o[t] = a.al_out[t];
+        s_al_i[t] = a.al_in[t];
+        s_rord[t] = (FWD && a.row_order) ? a.row_order[t] : (uint16_t)t;
+    }
+    if (FWD)
+        for (uint32_t t = tid; t < ngrp * NCo * Rp; t += blockDim.x) s_q[t] = 0.f;
+    __syncthreads();
+
+    if (warp == 0) {
+        // =========================== producer ===========================
+        uint32_t seq = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            uint32_t b_out = 0, b_in0 = 0;
+            if (lane == 0) {
+                const uint32_t lo = item & ((1u << n_bcast) - 1u), sh = item >> n_bcast;
+                if (FWD) {
+                    b_out = sh | (lo << a.n_sh);
+                    b_in0 = dev_pdep(sh, a.shared_mask);
+                } else {
+                    b_out = dev_pdep(sh, a.shared_mask) | dev_pdep(lo, a.free_mask);
+                    b_in0 = sh;
+                }
+            }
+            b_out = __shfl_sync(0xffffffffu, b_out, 0);
+            b_in0 = __shfl_sync(0xffffffffu, b_in0, 0);
+            uint32_t subm = 0;
+            for (uint32_t j = 0; j < nload; ++j, ++seq) {
+                const uint32_t s = seq % n_stages;
+                const uint32_t par = ((seq / n_stages) & 1u) ^ 1u;
+                const bool is_beta = FWD && (j == nred);
+                const uint32_t bk = is_beta ? b_out : (FWD ? (b_in0 | subm) : (b_in0 | (j << a.n_sh)));
+                subm = (subm - a.free_mask) & a.free_mask;
+                if (lane == 0) mbar_wait(&s_empty[s], par);
+                __syncwarp();
+                TmaStageMeta *m = &s_meta[s];
+                if (lane == 0) {
+                    const float *src = (is_beta ? a.beta : a.in) + (uint64_t)bk * BS;
+                    const uint32_t bytes = is_beta ? RR * 4u : BS * 4u;
+                    mbar_expect_tx(&s_full[s], bytes);
+                    bulk_g2s(smem_raw + L.off_stage + s * stage_bytes, src, bytes, &s_full[s]);
+                    m->b_out = b_out;
+                    m->b_self = bk;
+                }
+                if (j == 0)
+                    for (uint32_t t = lane; t < fgs_o; t += 32) m->fg_out[t] = a.fg_out[(uint64_t)b_out * fgs_o + t];
+                if (!FWD)
+                    for (uint32_t t = lane; t < fgs_i; t += 32) m->fg_self[t] = a.fg_in[(uint64_t)bk * fgs_i + t];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_full[s]);
+            }
+        }
+        return;
+    }
+
+    // =========================== consumers ===========================
+    const uint32_t ctid = tid - 32, cwarp = warp - 1;
+    const uint32_t sub = lane / G, gl = lane % G;
+    const uint32_t grp = cwarp * rpi + sub;
+    float *s_acc = reinterpret_cast<float *>(smem_raw + L.off_acc);
+    float *s_colred = reinterpret_cast<float *>(smem_raw + L.off_colred);
+    float *s_totred = reinterpret_cast<float *>(smem_raw + L.off_totred);
+    float *s_fgo = reinterpret_cast<float *>(smem_raw + L.off_fgo);
+
+    const float inv = (float)(1.0 / *a.in_scale);
+    const float cA = (float)a.tA * inv, cB = (float)a.tB * inv, cC = (float)a.tC * inv;
+    const uint32_t ccol = gl * 4;                 // this lane's 4 columns
+    const bool cok = ccol < R;
+    uint32_t a2o[4], a2i[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        a2o[v] = cok ? s_al_o[ccol + v] : 0u;
+        a2i[v] = cok ? s_al_i[ccol + v] : 0u;
+    }
+    float qc[4] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t cur_cls = 0xffffffffu;
+    float cta_sum = 0.f, sacc = 0.f;
+    const uint32_t n_iter = (R + ngrp - 1) / ngrp;
+    uint32_t seq = 0, parity_item = 0;
+
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, parity_item ^= 1u) {
+        uint32_t s0 = seq % n_stages;
+        mbar_wait(&s_full[s0], (seq / n_stages) & 1u);
+        const TmaStageMeta *m0 = &s_meta[s0];
+        const uint32_t b_out = m0->b_out;
+        const float *xs = reinterpret_cast<const float *>(smem_raw + L.off_stage + s0 * stage_bytes);
+        const float *fgo = m0->fg_out;
+        bool pre_weighted = false;
+        if (nred > 1) {
+            // fold the reduce set into s_acc; every thread owns the same elements for all k
+            for (uint32_t k = 0; k < nred; ++k) {
+                const uint32_t sk = (seq + k) % n_stages;
+                if (k > 0) mbar_wait(&s_full[sk], ((seq + k) / n_stages) & 1u);
+                const float *st = reinterpret_cast<const float *>(smem_raw + L.off_stage + sk * stage_bytes);
+                const float *fgk = s_meta[sk].fg_self;
+                for (uint32_t it = 0; it < n_iter; ++it) {
+                    const uint32_t ridx = it * ngrp + grp;
+                    if (ridx < R && cok) {
+                        float4 v = *reinterpret_cast<const float4 *>(st + ridx * R + ccol);
+                        if (!FWD) {
+                            const float fk = fgk[s_al_i[ridx]];
+                            v.x *= fk * fgk[NCi + a2i[0]];
+                            v.y *= fk * fgk[NCi + a2i[1]];
+                            v.z *= fk * fgk[NCi + a2i[2]];
+                            v.w *= fk * fgk[NCi + a2i[3]];
+                        }
+                        float4 *dst = reinterpret_cast<float4 *>(s_acc + ridx * R + ccol);
+                        if (k > 0) {
+                            const float4 o = *dst;
+                            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                        }
+                        *dst = v;
+                    }
+                }
+                // side sums: row/col/total records sit behind the values
+                for (uint32_t t = ctid; t < 2 * R + 1; t += 32 * kTmaConsumerWarps) {
+                    const float v = st[RR + t];
+                    s_acc[RR + t] = (k > 0 ? s_acc[RR + t] : 0.f) + v;
+                }
+                // stage 0 also carries the item's F/G vector: keep a copy, then every stage can go back at once
+                // (the reduce set may be longer than the ring, so nothing may be held across it)
+                if (k == 0)
+                    for (uint32_t t = ctid; t < fgs_o; t += 32 * kTmaConsumerWarps) s_fgo[t] = m0->fg_out[t];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[sk]);
+            }
+            consumer_bar();   // side sums and the F/G copy were written by other threads
+            fgo = s_fgo;
+            xs = s_acc;
+            pre_weighted = true;
+        }
+        const float *bs = nullptr;
+        uint32_t sb = 0;
+        if (FWD) {
+            sb = (seq + nred) % n_stages;
+            mbar_wait(&s_full[sb], ((seq + nred) / n_stages) & 1u);
+            bs = reinterpret_cast<const float *>(smem_raw + L.off_stage + sb * stage_bytes);
+        }
+        // ---- per-lane hoisted column quantities
+        const float ctot = cC * xs[RR + 2 * R];
+        float cbase[4], gout[4], gin0[4], colacc[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            cbase[v] = cok ? cB * xs[RR + R + ccol + v] + ctot : 0.f;
+            gout[v] = fgo[NCo + a2o[v]];
+            gin0[v] = (!FWD && !pre_weighted) ? m0->fg_self[NCi + a2i[v]] : 1.f;
+            colacc[v] = 0.f;
+        }
+        float totacc = 0.f;
+        float *outp = a.out + (uint64_t)b_out * BS;
+
+#pragma unroll 2
+        for (uint32_t it = 0; it < n_iter; ++it) {
+            const uint32_t ridx = it * ngrp + grp;
+            const bool rvalid = ridx < R;
+            const uint32_t R1 = rvalid ? s_rord[ridx] : 0u;
+            const uint32_t a1o = s_al_o[R1];
+            const float fo = fgo[a1o];
+            float rs = 0.f;
+            if (FWD && a1o != cur_cls) {
+                if (cur_cls != 0xffffffffu && cok) {
+                    float4 *qd = reinterpret_cast<float4 *>(s_q + (grp * NCo + cur_cls) * Rp + ccol);
+                    float4 o = *qd;
+                    o.x += qc[0]; o.y += qc[1]; o.z += qc[2]; o.w += qc[3];
+                    *qd = o;
+                    qc[0] = qc[1] = qc[2] = qc[3] = 0.f;
+                }
+                cur_cls = a1o;
+            }
+            if (rvalid && cok) {
+                const float4 xv = *reinterpret_cast<const float4 *>(xs + R1 * R + ccol);
+                const float rowterm = cB * xs[RR + R1];
+                float x[4] = {xv.x, xv.y, xv.z, xv.w};
+                if (!FWD && !pre_weighted) {
+                    const float fk = m0->fg_self[s_al_i[R1]];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) x[v] *= fk * gin0[v];
+                }
+                float o[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float base = cA * x[v] + rowterm + cbase[v];
+                    float w;
+                    if (FWD) {
+                        o[v] = (fo * gout[v]) * base;
+                        w = o[v];
+                    } else {
+                        o[v] = (a1o != 0 && a2o[v] != 0) ? base : 0.f;
+                        w = o[v] * (fo * gout[v]);
+                        sacc += o[v];
+                    }
+                    rs += w;
+                    colacc[v] += w;
+                }
+                *reinterpret_cast<float4 *>(outp + R1 * R + ccol) = make_float4(o[0], o[1], o[2], o[3]);
+                if (FWD) {
+                    const float4 bv = *reinterpret_cast<const float4 *>(bs + R1 * R + ccol);
+                    qc[0] += o[0] * bv.x; qc[1] += o[1] * bv.y; qc[2] += o[2] * bv.z; qc[3] += o[3] * bv.w;
+                }
+            }
+            for (uint32_t o = G >> 1; o; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+            if (gl == 0 && rvalid) {
+                outp[RR + R1] = rs;
+                totacc += rs;
+            }
+        }
+        // ---- hand the stages back
+        __syncwarp();
+        if (lane == 0) {
+            if (nred == 1) mbar_arrive(&s_empty[s0]);
+            if (FWD) mbar_arrive(&s_empty[sb]);
+        }
+        seq += nload;
+        // ---- column sums across the row groups (double-buffered scratch: one barrier per item)
+        float *cr = s_colred + parity_item * ngrp * Rp;
+        float *tr = s_totred + parity_item * ngrp;
+        if (cok) *reinterpret_cast<float4 *>(cr + grp * Rp + ccol) = make_float4(colacc[0], colacc[1], colacc[2], colacc[3]);
+        if (gl == 0) tr[grp] = totacc;
+        consumer_bar();
+        for (uint32_t t = ctid; t < R; t += 32 * kTmaConsumerWarps) {
+            float cs = 0.f;
+            for (uint32_t g = 0; g < ngrp; ++g) cs += cr[g * Rp + t];
+            outp[RR + R + t] = cs;
+        }
+        if (ctid == 0) {
+            float ts = 0.f;
+            for (uint32_t g = 0; g < ngrp; ++g) ts += tr[g];
+            outp[RR + 2 * R] = ts;
+            cta_sum += ts;
+        }
+    }
+
+    // ---- kernel epilogue (consumer threads only)
+    float *mypart = a.partial + (uint64_t)blockIdx.x * kPartialStride;
+    const uint32_t nct = 32 * kTmaConsumerWarps;
+    if (FWD) {
+        if (cur_cls != 0xffffffffu && cok) {
+            float4 *qd = reinterpret_cast<float4 *>(s_q + (grp * NCo + cur_cls) * Rp + ccol);
+            float4 o = *qd;
+            o.x += qc[0]; o.y += qc[1]; o.z += qc[2]; o.w += qc[3];
+            *qd = o;
+        }
+        consumer_bar();
+        for (uint32_t idx = ctid; idx < NCo * R; idx += nct) {
+            const uint32_t cls = idx / R, t = idx % R;
+            float v = 0.f;
+            for (uint32_t g = 0; g < ngrp; ++g) v += s_q[(g * NCo + cls) * Rp + t];
+            s_q[cls * Rp + t] = v;
+        }
+        consumer_bar();
+        for (uint32_t p = ctid; p < NCo * NCo; p += nct) {
+            const uint32_t i = p / NCo, j = p % NCo;
+            float w = 0.f;
+            for (uint32_t t = 0; t < R; ++t)
+                if (s_al_o[t] == j) w += s_q[i * Rp + t];
+            mypart[p] = w;
+        }
+        if (ctid == 0) mypart[kMaxClasses * kMaxClasses] = cta_sum;
+    } else {
+        for (uint32_t o = 16; o; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        consumer_bar();
+        if (lane == 0) s_totred[cwarp] = sacc;
+        consumer_bar();
+        if (ctid == 0) {
+            float ts = 0.f;
+            for (uint32_t w = 0; w < kTmaConsumerWarps; ++w) ts += s_totred[w];
+            mypart[kMaxClasses * kMaxClasses] = ts;
+        }
+    }
+    __threadfence();
+    consumer_bar();
+    if (ctid == 0) {
+        const unsigned int ticket = atomicAdd(a.counter, 1u);
+        s_last = (ticket == gridDim.x - 1);
+    }
+    consumer_bar();
+    if (!s_last) return;
+    __threadfence();
+    const uint32_t npair = FWD ? NCo * NCo : 0u;
+    for (uint32_t p = ctid; p < npair + 1; p += nct) {
+        const uint32_t slot = (p == npair) ? (uint32_t)(kMaxClasses * kMaxClasses) : p;
+        double acc = 0.0;
+        for (uint32_t blk = 0; blk < gridDim.x; ++blk) acc += (double)__ldcg(a.partial + (uint64_t)blk * kPartialStride + slot);
+        s_W[slot] = acc;
+    }
+    consumer_bar();
+    if (ctid == 0) {
+        *a.out_scale = s_W[kMaxClasses * kMaxClasses];
+        *a.counter = 0u;
+        if (FWD) {
+            const uint32_t nA = a.nA_out, ng = nA * (nA + 1) / 2;
+            for (uint32_t g = 0; g < ng; ++g) s_L[g] = 0.0;
+            double norm = 0.0;
+            for (uint32_t i = 1; i <= nA; ++i)
+                for (uint32_t j = 1; j <= nA; ++j) {
+                    const double w = s_W[i * NCo + j];
+                    s_L[(i - 1) + (j - 1) * j / 2] += w;
+                    norm += w;
+                }
+            for (uint32_t g = 0; g < ng; ++g) a.result[g] = s_L[g] / norm;
+        }
+    }
+}
+
+}  // namespace gg

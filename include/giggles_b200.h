@@ -76,8 +76,8 @@ typedef struct gg_problem {
 typedef struct gg_options {
     int32_t device;                   /* CUDA ordinal; -1 = current device      */
     uint64_t state_budget_bytes;      /* HBM budget for alpha/beta columns; 0 = 80 % of free memory */
-    int32_t kernel_variant;           /* 0 = auto; >0 forces a kernel variant (tests/profiling) */
-    int32_t reserved;
+    int32_t precision;                /* 0 = fp32 state with per-column scaling (production); 1 = fp64 state (validation) */
+    int32_t kernel_variant;           /* 0 = auto; 1 = generic step kernel only (no bulk-copy pipeline), for A/B tests */
 } gg_options;
 
 typedef struct gg_result gg_result;   /* host-side result table                 */
@@ -97,6 +97,10 @@ typedef struct gg_stats {
     uint32_t checkpoint_levels;
     float last_sweep_ms;              /* CUDA-event time of the last sweep      */
     float last_fwdbwd_kernel_ms;      /* summed time of the column-step kernels in the last timed sweep (0 if not timed) */
+    float last_fwd_ms;                /* ... of which forward step launches (timed sweeps only) */
+    float last_bwd_ms;                /* ... backward step launches                             */
+    float last_emit_ms;               /* emission-table launches                                */
+    float reserved;
 } gg_stats;
 
 /* ---- one-shot call: replaces `new GenotypeHMM(...)` (giggles/core.pyx:498 ->
@@ -124,6 +128,8 @@ uint32_t gg_result_n_columns(const gg_result *r);
 /* flat view: all columns back to back, offsets[c]..offsets[c+1]              */
 const double *gg_result_flat(const gg_result *r, const uint64_t **offsets);
 void gg_result_free(gg_result *r);
+/* wraps caller-provided posteriors (e.g. gathered from other ranks) so gg_result_call can be applied to them */
+gg_result *gg_result_from_host(uint32_t n_columns, const uint64_t *offsets, const double *values);
 
 /* ---- column structure, for the bit-identical-structure parity test.  Mirrors
  *      Column::Column (src/column.cpp:10-39) and
@@ -147,6 +153,10 @@ void gg_plan_free(gg_plan *pl);
 /* ---- host helpers that define the kernel's inputs bit-for-bit ---- */
 /* Entry::set_emission_score (src/entry.cpp:50-64): p_i = 10^-reg + 1/sum_j base^(e_j-e_i), normalised. */
 void gg_entry_emission(const double *scores, uint32_t n, int32_t reg_const, double base_const, double *out);
+/* the same for many entries at once: entry e has scores[offsets[e] .. offsets[e+1]) (what
+ * Read::addVariant does per call, src/read.cpp:69-71) */
+void gg_entry_emission_batch(const double *scores, const uint64_t *offsets, uint64_t n_entries, int32_t reg_const,
+                             double base_const, double *out);
 /* TransitionProbabilityComputer (src/transitionprobabilitycomputer.cpp:10-15). */
 void gg_transition_scalars(float recombcost, uint32_t n_haps, double *pr, double *qr);
 /* binomial_coefficient (src/binomial.cpp:5-15). */
@@ -158,6 +168,13 @@ int32_t gg_binomial_coefficient(int32_t n, int32_t k);
  *      when undefined, gl_log10 flat like gg_result_flat (floored at -1000). */
 int gg_result_call(const gg_result *r, double gt_qual_threshold, int32_t *gt_index,
                    int32_t *gq, double *gl_log10);
+
+/* ---- checkpoint schedule dry run (host only, no device): builds and self-checks the launch
+ *      schedule gg_hmm_create would use for columns of the given byte sizes under `budget`.
+ *      The reference's fixed sqrt(C) schedule is src/genotypehmm.cpp:130,153-156,364-383. */
+int gg_schedule_dry_run(uint32_t n_columns, const uint64_t *col_bytes, const uint64_t *fg_bytes, uint64_t budget,
+                        uint64_t *arena_bytes, uint32_t *levels, uint64_t *n_bwd, uint64_t *n_fwd,
+                        char *err, size_t errlen);
 
 const char *gg_version(void);
 int gg_device_count(void);
