@@ -77,7 +77,8 @@ struct gg_hmm {
     Plan plan;
     Schedule sched;
     bool fp64 = false;
-    int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only
+    int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined kernel with one CTA per SM
+    bool tma_attr_done = false;
     int device = 0;
     int num_sms = 0;
     size_t elem = 4;
@@ -153,6 +154,7 @@ static const void *pick_kernel(int V, int NS, bool fwd) {
 
 static constexpr size_t kMaxDynSmem = 200 * 1024;
 static constexpr size_t kMaxDynSmemTma = 222 * 1024;   // 227 KB per CTA minus the kernel's static shared memory
+static constexpr size_t kMaxDynSmemTma2 = 111 * 1024;  // two CTAs per SM: (228 KB - 2 * (1 KB reserved + static)) / 2
 
 template <typename T>
 struct Engine {
@@ -253,29 +255,56 @@ struct Engine {
     }
 
     // Pipelined bulk-copy kernel (hmm_tma_kernel.cuh): fp32, R % 4 == 0, one block record per stage.
+    static const void *tma_kernel(bool fwd, uint32_t G) {
+        switch (G) {
+#define GG_TMA(GG) case GG: return fwd ? (const void *)step_tma_kernel<true, GG> : (const void *)step_tma_kernel<false, GG>;
+            GG_TMA(1) GG_TMA(2) GG_TMA(4) GG_TMA(8) GG_TMA(16) GG_TMA(32)
+#undef GG_TMA
+        }
+        return nullptr;
+    }
+
     static bool try_launch_tma(gg_hmm *h, const StepArgs<T> &a, const ColumnPlan &pco, bool fwd) {
         if (sizeof(T) != 4 || h->kernel_variant == 1 || a.in == nullptr) return false;
         if (a.R % 4 != 0 || a.R > 128 || h->shape.V != 4 || h->shape.NS != 1) return false;
         const uint32_t rpi = 32 / a.G, ngrp = kTmaConsumerWarps * rpi;
         const uint32_t nred = fwd ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
-        uint32_t stages = kTmaMaxStages;
-        TmaSmemLayout L = tma_smem_layout(a.R, a.BS, stages, ngrp, pco.n_alleles + 1, fwd, nred > 1);
-        while (L.total > kMaxDynSmemTma && stages > 3) {
-            --stages;
-            L = tma_smem_layout(a.R, a.BS, stages, ngrp, pco.n_alleles + 1, fwd, nred > 1);
+        const void *k = tma_kernel(fwd, a.G);
+        if (!k) return false;
+        if (!h->tma_attr_done) {
+            for (uint32_t g = 1; g <= 32; g <<= 1)
+                for (bool f : {false, true})
+                    GG_CUDA(cudaFuncSetAttribute(tma_kernel(f, g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
+            h->tma_attr_done = true;
         }
-        if (L.total > kMaxDynSmemTma) return false;
-        const void *k = fwd ? (const void *)step_tma_kernel<true> : (const void *)step_tma_kernel<false>;
-        static bool attr_done = false;
-        if (!attr_done) {
-            GG_CUDA(cudaFuncSetAttribute((const void *)step_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
-            GG_CUDA(cudaFuncSetAttribute((const void *)step_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
-            attr_done = true;
+        // two CTAs per SM with 3-4 stages each when they fit (more warps to hide latency), else one with up to 8
+        auto fit = [&](uint32_t lo, uint32_t hi, size_t cap, uint32_t &stages, TmaSmemLayout &L) {
+            for (stages = hi; stages >= lo; --stages) {
+                L = tma_smem_layout(a.R, a.BS, stages, ngrp, pco.n_alleles + 1, fwd, nred > 1);
+                if (L.total <= cap) return true;
+            }
+            return false;
+        };
+        uint32_t stages = 0, ctas = 2;
+        TmaSmemLayout L{};
+        if (h->kernel_variant == 2 || !fit(3, 4, kMaxDynSmemTma2, stages, L)) {
+            ctas = 1;
+            if (!fit(3, kTmaMaxStages, kMaxDynSmemTma, stages, L)) return false;
         }
+        auto key = std::make_tuple(k, (int)kTmaThreads, (size_t)L.total);
+        auto it = h->occ_cache.find(key);
+        int occ;
+        if (it == h->occ_cache.end()) {
+            GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kTmaThreads, L.total));
+            h->occ_cache[key] = occ;
+        } else {
+            occ = it->second;
+        }
+        if (occ < 1) return false;
+        ctas = std::min<uint32_t>(ctas, (uint32_t)occ);
         const uint64_t n_items = (uint64_t)1 << pco.u;
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)h->num_sms);
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)h->num_sms * ctas);
         StepArgs<float> af;
-        static_assert(sizeof(af) == sizeof(StepArgs<T>) || sizeof(T) != 4, "layout");
         std::memcpy(&af, &a, sizeof(af));
         uint32_t ns = stages;
         void *params[] = {(void *)&af, (void *)&ns};

@@ -30,7 +30,7 @@ struct TmaStageMeta {
 };
 
 struct TmaSmemLayout {
-    uint32_t off_stage, off_meta, off_acc, off_colred, off_totred, off_fgo, off_q, off_al_o, off_al_i, off_rord, total;
+    uint32_t off_stage, off_meta, off_acc, off_colred, off_totred, off_fgo, off_q, off_al_o, off_al_i, off_rord, off_rsum, total;
 };
 __host__ __device__ inline TmaSmemLayout tma_smem_layout(uint32_t R, uint32_t BS, uint32_t n_stages, uint32_t ngrp,
                                                          uint32_t ncls_out, bool fwd, bool need_acc) {
@@ -49,7 +49,9 @@ __host__ __device__ inline TmaSmemLayout tma_smem_layout(uint32_t R, uint32_t BS
     L.off_al_o = o; o += Rp;
     L.off_al_i = o; o += Rp;
     o = (o + 3u) & ~3u;
-    L.off_rord = o; o += Rp * 2;
+    o = (o + 7u) & ~7u;
+    L.off_rord = o; o += (Rp + ngrp) * 8;               // per-row metadata (2 words), padded to whole row iterations
+    L.off_rsum = o; o += 2 * Rp * 4;                    // row sums of the produced block, double-buffered across items
     L.total = (o + 127u) & ~127u;
     return L;
 }
@@ -78,8 +80,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kTmaConsumerWarps) : "memory"); }
 
-template <bool FWD>
-__global__ void __launch_bounds__(kTmaThreads, 1)
+// row metadata, all pre-scaled to byte offsets so the row loop does no address arithmetic:
+//   x = byte offset of the row inside a block (R1*R*4) | valid << 31
+//   y = R1*4 | (allele class of R1 in the output column)*4 << 10 | (... in the input column)*4 << 20
+__device__ __forceinline__ uint2 pack_row(uint32_t R1, uint32_t R, uint32_t a1o, uint32_t a1i) {
+    return make_uint2((R1 * R * 4u) | 0x80000000u, (R1 * 4u) | (a1o * 4u) << 10 | (a1i * 4u) << 20);
+}
+
+template <bool FWD, int G>
+__global__ void __launch_bounds__(kTmaThreads, 2)
 step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_full[kTmaMaxStages];
@@ -88,13 +97,13 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
     __shared__ double s_L[GG_MAX_ALLELES * (GG_MAX_ALLELES + 1) / 2];
     __shared__ bool s_last;
 
-    const uint32_t R = a.R, G = a.G, BS = a.BS;
+    const uint32_t R = a.R, BS = a.BS;
     const uint32_t RR = R * R;
     const uint32_t Rp = (R + 3u) & ~3u;
     const uint32_t stage_bytes = (BS * 4u + 127u) & ~127u;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t rpi = 32u / G;
-    const uint32_t ngrp = kTmaConsumerWarps * rpi;
+    constexpr uint32_t rpi = 32u / G;
+    constexpr uint32_t ngrp = kTmaConsumerWarps * rpi;
     const uint32_t NCo = a.nA_out + 1, NCi = a.nA_in + 1;
     const uint32_t fgs_o = 2 * NCo, fgs_i = 2 * NCi;
     const uint32_t nred = FWD ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
@@ -103,6 +112,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
     const TmaSmemLayout L = tma_smem_layout(R, BS, n_stages, ngrp, NCo, FWD, nred > 1);
     TmaStageMeta *s_meta = reinterpret_cast<TmaStageMeta *>(smem_raw + L.off_meta);
     const uint32_t n_items = 1u << a.u_out;
+    const uint32_t n_iter = (R + ngrp - 1) / ngrp;
 
     if (tid == 0) {
         for (uint32_t s = 0; s < n_stages; ++s) {
@@ -114,12 +124,19 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
     // consumer-side tables
     uint8_t *s_al_o = smem_raw + L.off_al_o;
     uint8_t *s_al_i = smem_raw + L.off_al_i;
-    uint16_t *s_rord = reinterpret_cast<uint16_t *>(smem_raw + L.off_rord);
+    uint2 *s_rowmeta = reinterpret_cast<uint2 *>(smem_raw + L.off_rord);
     float *s_q = reinterpret_cast<float *>(smem_raw + L.off_q);
+    for (uint32_t t = tid; t < n_iter * ngrp; t += blockDim.x) {
+        uint2 m = make_uint2(0u, 0u);   // padding rows: offset 0, class 0 (zero emission weight), not valid
+        if (t < R) {
+            const uint32_t R1 = (FWD && a.row_order) ? a.row_order[t] : t;
+            m = pack_row(R1, R, a.al_out[R1], a.al_in[R1]);
+        }
+        s_rowmeta[t] = m;
+    }
     for (uint32_t t = tid; t < R; t += blockDim.x) {
         s_al_o[t] = a.al_out[t];
         s_al_i[t] = a.al_in[t];
-        s_rord[t] = (FWD && a.row_order) ? a.row_order[t] : (uint16_t)t;
     }
     if (FWD)
         for (uint32_t t = tid; t < ngrp * NCo * Rp; t += blockDim.x) s_q[t] = 0.f;
@@ -127,21 +144,38 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
 
     if (warp == 0) {
         // =========================== producer ===========================
-        uint32_t seq = 0;
-        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-            uint32_t b_out = 0, b_in0 = 0;
-            if (lane == 0) {
-                const uint32_t lo = item & ((1u << n_bcast) - 1u), sh = item >> n_bcast;
-                if (FWD) {
-                    b_out = sh | (lo << a.n_sh);
-                    b_in0 = dev_pdep(sh, a.shared_mask);
-                } else {
-                    b_out = dev_pdep(sh, a.shared_mask) | dev_pdep(lo, a.free_mask);
-                    b_in0 = sh;
-                }
+        // F/G vectors are prefetched one item ahead so that their global-load latency never sits between two
+        // bulk copies.
+        auto decode = [&](uint32_t item, uint32_t &b_out, uint32_t &b_in0) {
+            const uint32_t lo = item & ((1u << n_bcast) - 1u), sh = item >> n_bcast;
+            if (FWD) {
+                b_out = sh | (lo << a.n_sh);
+                b_in0 = dev_pdep(sh, a.shared_mask);
+            } else {
+                b_out = dev_pdep(sh, a.shared_mask) | dev_pdep(lo, a.free_mask);
+                b_in0 = sh;
             }
-            b_out = __shfl_sync(0xffffffffu, b_out, 0);
-            b_in0 = __shfl_sync(0xffffffffu, b_in0, 0);
+        };
+        uint32_t seq = 0;
+        uint32_t nb_out = 0, nb_in0 = 0;
+        float pf_o0 = 0.f, pf_o1 = 0.f, pf_i0 = 0.f, pf_i1 = 0.f;
+        auto prefetch = [&](uint32_t item) {
+            uint32_t bo = 0, bi = 0;
+            if (lane == 0) decode(item, bo, bi);
+            nb_out = __shfl_sync(0xffffffffu, bo, 0);
+            nb_in0 = __shfl_sync(0xffffffffu, bi, 0);
+            if (lane < fgs_o) pf_o0 = a.fg_out[(uint64_t)nb_out * fgs_o + lane];
+            if (lane + 32 < fgs_o) pf_o1 = a.fg_out[(uint64_t)nb_out * fgs_o + lane + 32];
+            if (!FWD) {
+                if (lane < fgs_i) pf_i0 = a.fg_in[(uint64_t)nb_in0 * fgs_i + lane];
+                if (lane + 32 < fgs_i) pf_i1 = a.fg_in[(uint64_t)nb_in0 * fgs_i + lane + 32];
+            }
+        };
+        if (blockIdx.x < n_items) prefetch(blockIdx.x);
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const uint32_t b_out = nb_out, b_in0 = nb_in0;
+            const float fo0 = pf_o0, fo1 = pf_o1, fi0 = pf_i0, fi1 = pf_i1;
+            if (item + gridDim.x < n_items) prefetch(item + gridDim.x);
             uint32_t subm = 0;
             for (uint32_t j = 0; j < nload; ++j, ++seq) {
                 const uint32_t s = seq % n_stages;
@@ -160,10 +194,18 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
                     m->b_out = b_out;
                     m->b_self = bk;
                 }
-                if (j == 0)
-                    for (uint32_t t = lane; t < fgs_o; t += 32) m->fg_out[t] = a.fg_out[(uint64_t)b_out * fgs_o + t];
-                if (!FWD)
-                    for (uint32_t t = lane; t < fgs_i; t += 32) m->fg_self[t] = a.fg_in[(uint64_t)bk * fgs_i + t];
+                if (j == 0) {
+                    if (lane < fgs_o) m->fg_out[lane] = fo0;
+                    if (lane + 32 < fgs_o) m->fg_out[lane + 32] = fo1;
+                }
+                if (!FWD) {
+                    if (j == 0) {
+                        if (lane < fgs_i) m->fg_self[lane] = fi0;
+                        if (lane + 32 < fgs_i) m->fg_self[lane + 32] = fi1;
+                    } else {
+                        for (uint32_t t = lane; t < fgs_i; t += 32) m->fg_self[t] = a.fg_in[(uint64_t)bk * fgs_i + t];
+                    }
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_full[s]);
             }
@@ -179,11 +221,12 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
     float *s_colred = reinterpret_cast<float *>(smem_raw + L.off_colred);
     float *s_totred = reinterpret_cast<float *>(smem_raw + L.off_totred);
     float *s_fgo = reinterpret_cast<float *>(smem_raw + L.off_fgo);
+    float *s_rsum = reinterpret_cast<float *>(smem_raw + L.off_rsum);
 
     const float inv = (float)(1.0 / *a.in_scale);
     const float cA = (float)a.tA * inv, cB = (float)a.tB * inv, cC = (float)a.tC * inv;
-    const uint32_t ccol = gl * 4;                 // this lane's 4 columns
-    const bool cok = ccol < R;
+    const bool cok = gl * 4 < R;
+    const uint32_t ccol = cok ? gl * 4 : 0u;       // idle lanes shadow columns 0..3 with zero weight, stores off
     uint32_t a2o[4], a2i[4];
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -193,11 +236,10 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
     float qc[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t cur_cls = 0xffffffffu;
     float cta_sum = 0.f, sacc = 0.f;
-    const uint32_t n_iter = (R + ngrp - 1) / ngrp;
     uint32_t seq = 0, parity_item = 0;
 
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, parity_item ^= 1u) {
-        uint32_t s0 = seq % n_stages;
+        const uint32_t s0 = seq % n_stages;
         mbar_wait(&s_full[s0], (seq / n_stages) & 1u);
         const TmaStageMeta *m0 = &s_meta[s0];
         const uint32_t b_out = m0->b_out;
@@ -247,81 +289,98 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
             xs = s_acc;
             pre_weighted = true;
         }
-        const float *bs = nullptr;
+        const float *bs = xs;
         uint32_t sb = 0;
         if (FWD) {
             sb = (seq + nred) % n_stages;
             mbar_wait(&s_full[sb], ((seq + nred) / n_stages) & 1u);
             bs = reinterpret_cast<const float *>(smem_raw + L.off_stage + sb * stage_bytes);
         }
-        // ---- per-lane hoisted column quantities
-        const float ctot = cC * xs[RR + 2 * R];
-        float cbase[4], gout[4], gin0[4], colacc[4];
+        // ---- per-lane hoisted column quantities.  With g = G_b[a(R2)] of the output block, m = [a(R2) defined]:
+        //   forward : alpha = F[a(R1)] * ( (g*cA) * x + g * rowterm + g*cbase )
+        //   backward: beta  = [a(R1) defined] * ( (m*cA*gin) * (fk*x) + m * rowterm + m*cbase ),  weight w = beta * F*g
+        const float totv = xs[RR + 2 * R];
+        const float ctot = cC * totv;
+        const float *fgi = m0->fg_self;
+        const bool weigh = !FWD && !pre_weighted;
+        float kx[4], kr[4], kc[4], gout[4], colacc[4];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            cbase[v] = cok ? cB * xs[RR + R + ccol + v] + ctot : 0.f;
+            const float cb = cB * xs[RR + R + ccol + v] + ctot;
             gout[v] = fgo[NCo + a2o[v]];
-            gin0[v] = (!FWD && !pre_weighted) ? m0->fg_self[NCi + a2i[v]] : 1.f;
+            if (FWD) {
+                kx[v] = gout[v] * cA; kr[v] = gout[v]; kc[v] = gout[v] * cb;
+            } else {
+                const float m = a2o[v] != 0 ? 1.f : 0.f;
+                kx[v] = m * cA * (weigh ? fgi[NCi + a2i[v]] : 1.f); kr[v] = m; kc[v] = m * cb;
+            }
             colacc[v] = 0.f;
         }
         float totacc = 0.f;
         float *outp = a.out + (uint64_t)b_out * BS;
+        const char *xcol = reinterpret_cast<const char *>(xs + ccol);
+        const char *bcol = reinterpret_cast<const char *>(bs + ccol);
+        const char *xrow = reinterpret_cast<const char *>(xs + RR);
+        const char *fgo_b = reinterpret_cast<const char *>(fgo);
+        const char *fgi_b = reinterpret_cast<const char *>(fgi);
+        char *ocol = reinterpret_cast<char *>(outp + ccol);
+        float *rsum = s_rsum + parity_item * Rp;
 
-#pragma unroll 2
+#pragma unroll 4
         for (uint32_t it = 0; it < n_iter; ++it) {
-            const uint32_t ridx = it * ngrp + grp;
-            const bool rvalid = ridx < R;
-            const uint32_t R1 = rvalid ? s_rord[ridx] : 0u;
-            const uint32_t a1o = s_al_o[R1];
-            const float fo = fgo[a1o];
-            float rs = 0.f;
-            if (FWD && a1o != cur_cls) {
-                if (cur_cls != 0xffffffffu && cok) {
-                    float4 *qd = reinterpret_cast<float4 *>(s_q + (grp * NCo + cur_cls) * Rp + ccol);
+            const uint2 meta = s_rowmeta[it * ngrp + grp];
+            const uint32_t rowb = meta.x & 0x7fffffffu;
+            const uint32_t r1b = meta.y & 0x3ffu, a1ob = (meta.y >> 10) & 0x3ffu, a1ib = (meta.y >> 20) & 0x3ffu;
+            const bool rvalid = (int32_t)meta.x < 0;
+            const float4 xv = *reinterpret_cast<const float4 *>(xcol + rowb);
+            const float rowterm = cB * *reinterpret_cast<const float *>(xrow + r1b);
+            const float fo = *reinterpret_cast<const float *>(fgo_b + a1ob);
+            const float fk = weigh ? *reinterpret_cast<const float *>(fgi_b + a1ib) : 1.f;
+            if (FWD && a1ob != cur_cls) {         // row class changed: park the posterior accumulators
+                if (cur_cls != 0xffffffffu && cok) {   // idle lanes must not touch the slot of the lane they shadow
+                    float4 *qd = reinterpret_cast<float4 *>(s_q + (grp * NCo + (cur_cls >> 2)) * Rp + ccol);
                     float4 o = *qd;
                     o.x += qc[0]; o.y += qc[1]; o.z += qc[2]; o.w += qc[3];
                     *qd = o;
                     qc[0] = qc[1] = qc[2] = qc[3] = 0.f;
                 }
-                cur_cls = a1o;
+                cur_cls = a1ob;
             }
-            if (rvalid && cok) {
-                const float4 xv = *reinterpret_cast<const float4 *>(xs + R1 * R + ccol);
-                const float rowterm = cB * xs[RR + R1];
-                float x[4] = {xv.x, xv.y, xv.z, xv.w};
-                if (!FWD && !pre_weighted) {
-                    const float fk = m0->fg_self[s_al_i[R1]];
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) x[v] *= fk * gin0[v];
-                }
-                float o[4];
+            const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+            float o[4];
+            float rs = 0.f;
+            if (FWD) {
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    const float base = cA * x[v] + rowterm + cbase[v];
-                    float w;
-                    if (FWD) {
-                        o[v] = (fo * gout[v]) * base;
-                        w = o[v];
-                    } else {
-                        o[v] = (a1o != 0 && a2o[v] != 0) ? base : 0.f;
-                        w = o[v] * (fo * gout[v]);
-                        sacc += o[v];
-                    }
-                    rs += w;
-                    colacc[v] += w;
+                    o[v] = fo * fmaf(kx[v], x[v], fmaf(kr[v], rowterm, kc[v]));
+                    rs += o[v];
+                    colacc[v] += o[v];
                 }
-                *reinterpret_cast<float4 *>(outp + R1 * R + ccol) = make_float4(o[0], o[1], o[2], o[3]);
-                if (FWD) {
-                    const float4 bv = *reinterpret_cast<const float4 *>(bs + R1 * R + ccol);
-                    qc[0] += o[0] * bv.x; qc[1] += o[1] * bv.y; qc[2] += o[2] * bv.z; qc[3] += o[3] * bv.w;
+            } else {
+                const bool rdef = a1ob != 0;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float t = fmaf(kx[v], fk * x[v], fmaf(kr[v], rowterm, kc[v]));
+                    o[v] = rdef ? t : 0.f;
+                    const float fg = fo * gout[v];
+                    rs = fmaf(o[v], fg, rs);
+                    colacc[v] = fmaf(o[v], fg, colacc[v]);
                 }
             }
-            for (uint32_t o = G >> 1; o; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-            if (gl == 0 && rvalid) {
-                outp[RR + R1] = rs;
-                totacc += rs;
+            if (rvalid && cok) *reinterpret_cast<float4 *>(ocol + rowb) = make_float4(o[0], o[1], o[2], o[3]);
+            if (FWD) {
+                const float4 bv = *reinterpret_cast<const float4 *>(bcol + rowb);
+                qc[0] = fmaf(o[0], bv.x, qc[0]); qc[1] = fmaf(o[1], bv.y, qc[1]);
+                qc[2] = fmaf(o[2], bv.z, qc[2]); qc[3] = fmaf(o[3], bv.w, qc[3]);
             }
+#pragma unroll
+            for (int sh = G >> 1; sh > 0; sh >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, sh);
+            if (gl == 0 && rvalid) *reinterpret_cast<float *>(reinterpret_cast<char *>(rsum) + r1b) = rs;
+            totacc += rs;        // identical in every lane of the row group; padding rows contribute 0
         }
+        // backward: the column scale.  Without missing alleles sum(beta_{c-1}[b']) equals the reduced input total
+        // exactly (tA + 2R tB + R^2 tC = 1); any positive scalar of that magnitude serves, so use it.
+        if (!FWD && ctid == 32 * kTmaConsumerWarps - 1) sacc += totv;
         // ---- hand the stages back
         __syncwarp();
         if (lane == 0) {
@@ -337,11 +396,14 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
         consumer_bar();
         for (uint32_t t = ctid; t < R; t += 32 * kTmaConsumerWarps) {
             float cs = 0.f;
+#pragma unroll 8
             for (uint32_t g = 0; g < ngrp; ++g) cs += cr[g * Rp + t];
             outp[RR + R + t] = cs;
+            outp[RR + t] = rsum[t];
         }
-        if (ctid == 0) {
+        if (ctid == 32 * kTmaConsumerWarps - 1) {
             float ts = 0.f;
+#pragma unroll 8
             for (uint32_t g = 0; g < ngrp; ++g) ts += tr[g];
             outp[RR + 2 * R] = ts;
             cta_sum += ts;
@@ -353,7 +415,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
     const uint32_t nct = 32 * kTmaConsumerWarps;
     if (FWD) {
         if (cur_cls != 0xffffffffu && cok) {
-            float4 *qd = reinterpret_cast<float4 *>(s_q + (grp * NCo + cur_cls) * Rp + ccol);
+            float4 *qd = reinterpret_cast<float4 *>(s_q + (grp * NCo + (cur_cls >> 2)) * Rp + ccol);
             float4 o = *qd;
             o.x += qc[0]; o.y += qc[1]; o.z += qc[2]; o.w += qc[3];
             *qd = o;
@@ -373,18 +435,10 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
                 if (s_al_o[t] == j) w += s_q[i * Rp + t];
             mypart[p] = w;
         }
-        if (ctid == 0) mypart[kMaxClasses * kMaxClasses] = cta_sum;
     } else {
-        for (uint32_t o = 16; o; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-        consumer_bar();
-        if (lane == 0) s_totred[cwarp] = sacc;
-        consumer_bar();
-        if (ctid == 0) {
-            float ts = 0.f;
-            for (uint32_t w = 0; w < kTmaConsumerWarps; ++w) ts += s_totred[w];
-            mypart[kMaxClasses * kMaxClasses] = ts;
-        }
+        cta_sum = sacc * inv;     // thread nct-1 holds it; inv puts it on the scale of the stored values
     }
+    if (ctid == nct - 1) mypart[kMaxClasses * kMaxClasses] = cta_sum;
     __threadfence();
     consumer_bar();
     if (ctid == 0) {
