@@ -81,7 +81,7 @@ class gg_stats(C.Structure):
 
 # every symbol include/giggles_b200.h declares (tests check that the library exports them all)
 SYMBOLS = [
-    "gg_hmm_run", "gg_hmm_create", "gg_hmm_sweep", "gg_hmm_fetch", "gg_hmm_stats", "gg_hmm_destroy",
+    "gg_hmm_run", "gg_hmm_create", "gg_hmm_sweep", "gg_hmm_fetch", "gg_hmm_stats", "gg_hmm_destroy", "gg_arena_release",
     "gg_result_likelihoods", "gg_result_n_columns", "gg_result_flat", "gg_result_free", "gg_result_call", "gg_result_from_host",
     "gg_plan_build", "gg_plan_n_columns", "gg_plan_active", "gg_plan_untagged", "gg_plan_shared_mask_prev",
     "gg_plan_compatible_prev", "gg_plan_free",

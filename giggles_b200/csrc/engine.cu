@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -64,6 +65,42 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
 };
 
+// One retired arena per device is kept for the next gg_hmm_create (cudaMalloc/cudaFree of a >100 GB arena costs
+// more than a sweep of a small window); gg_arena_release() frees it.
+struct ArenaCache {
+    std::mutex mu;
+    std::map<int, std::pair<unsigned char *, size_t>> slot;
+    unsigned char *take(int dev, size_t need, size_t &got) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = slot.find(dev);
+        if (it == slot.end()) return nullptr;
+        unsigned char *p = it->second.first;
+        size_t n = it->second.second;
+        slot.erase(it);
+        if (n >= need && n <= need + need / 2 + (64u << 20)) {
+            got = n;
+            return p;
+        }
+        cudaFree(p);
+        return nullptr;
+    }
+    void give(int dev, unsigned char *p, size_t n) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = slot.find(dev);
+        if (it != slot.end()) {
+            cudaFree(it->second.first);
+            slot.erase(it);
+        }
+        slot[dev] = {p, n};
+    }
+    void clear() {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto &kv : slot) cudaFree(kv.second.first);
+        slot.clear();
+    }
+};
+static ArenaCache g_arena_cache;
+
 struct LaunchShape {
     int V, NS;
     uint32_t G, nwarps_fwd, nwarps_bwd;
@@ -88,7 +125,9 @@ struct gg_hmm {
     DevBuf<uint8_t> d_em_side, d_allele1;
     DevBuf<double> d_em_prob, d_scale_a, d_scale_b, d_result;
     DevBuf<uint16_t> d_row_order;
-    DevBuf<unsigned char> d_arena, d_partial;
+    DevBuf<unsigned char> d_partial;
+    unsigned char *arena = nullptr;
+    size_t arena_bytes = 0;
     DevBuf<unsigned int> d_counter;
     uint32_t max_grid = 0;
     LaunchShape shape{};
@@ -98,6 +137,7 @@ struct gg_hmm {
     ~gg_hmm() {
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
+        if (arena) g_arena_cache.give(device, arena, arena_bytes);
     }
 };
 
@@ -167,7 +207,7 @@ struct Engine {
         const uint32_t R = pl.n_haps;
         const uint32_t co = op.c;
         const ColumnPlan &pco = pl.cols[co];
-        unsigned char *arena = h->d_arena.p;
+        unsigned char *arena = h->arena;
         StepArgs<T> a{};
         a.R = R;
         a.G = h->shape.G;
@@ -316,7 +356,7 @@ struct Engine {
     static void launch_emit(gg_hmm *h, const Op &op) {
         const Plan &pl = h->plan;
         uint32_t lo = op.c;
-        T *region = reinterpret_cast<T *>(h->d_arena.p + op.out_off);
+        T *region = reinterpret_cast<T *>(h->arena + op.out_off);
         const uint64_t prefix_lo = h->fg_prefix_elems[op.c];
         while (lo <= op.hi) {
             const uint32_t n = std::min<uint32_t>(op.hi - lo + 1, 32768);
@@ -401,7 +441,11 @@ struct Engine {
             const std::string m = e.what();
             throw CudaError(m.find("budget") != std::string::npos ? GG_ERR_NOMEM : GG_ERR_INVALID, m);
         }
-        h->d_arena.alloc(h->sched.arena_bytes);
+        h->arena = g_arena_cache.take(h->device, h->sched.arena_bytes, h->arena_bytes);
+        if (!h->arena && h->sched.arena_bytes) {
+            GG_CUDA(cudaMalloc(&h->arena, h->sched.arena_bytes));
+            h->arena_bytes = h->sched.arena_bytes;
+        }
         GG_CUDA(cudaStreamSynchronize(h->stream));
         // stats that do not depend on a sweep
         gg_stats &st = h->stats;
@@ -576,6 +620,8 @@ void gg_hmm_destroy(gg_hmm *h) {
     cudaSetDevice(h->device);
     delete h;
 }
+
+void gg_arena_release(void) { g_arena_cache.clear(); }
 
 int gg_hmm_run(const gg_problem *p, const gg_options *o, gg_result **out, char *err, size_t errlen) {
     if (out) *out = nullptr;

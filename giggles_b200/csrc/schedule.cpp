@@ -120,11 +120,14 @@ struct Builder {
             if (ok) { ends.swap(e); break; }
         }
         if (ends.empty()) {
-            // too tight for one extra level: spend half of what is left on checkpoints, recurse into the parts
-            uint64_t nck = (avail / 2) / std::max<uint64_t>(maxcol, 1);
-            if (nck < 1 || avail < nck * maxcol + roll + 2 * maxcol)
+            // too tight for one extra level: spend about half of what is left on checkpoints and recurse into the
+            // parts, always leaving them room for two rolling columns plus two more (a part can then split again)
+            const uint64_t M = avail > 2 * maxfg ? (avail - 2 * maxfg) / std::max<uint64_t>(maxcol, 1) : 0;
+            if (M < 5)
                 throw std::runtime_error("state budget too small for this problem: " + std::to_string(avail) +
                                          " bytes left for a range whose largest column takes " + std::to_string(maxcol));
+            uint64_t nck = M / 2;
+            if (M - nck < 4) nck = M - 4;
             uint32_t m = (uint32_t)std::min<uint64_t>(nck + 1, ncols);
             for (uint32_t j = 1; j <= m; ++j) ends.push_back(lo + (uint32_t)((uint64_t)ncols * j / m) - 1);
         }

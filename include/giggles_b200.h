@@ -117,6 +117,9 @@ int gg_hmm_sweep(gg_hmm *h, int timed_kernels, char *err, size_t errlen); /* bac
 int gg_hmm_fetch(gg_hmm *h, gg_result **out, char *err, size_t errlen);    /* D2H posteriors        */
 int gg_hmm_stats(const gg_hmm *h, gg_stats *s);
 void gg_hmm_destroy(gg_hmm *h);
+/* gg_hmm_destroy keeps the state arena of the last handle per device for the next gg_hmm_create / gg_hmm_run
+ * (allocating >100 GB costs more than sweeping a small chromosome); this frees it. */
+void gg_arena_release(void);
 
 /* ---- result access: replaces GenotypeHMM::get_genotype_likelihoods
  *      (src/genotypehmm.cpp:563-574, giggles/core.pyx:505-506).  Returns a pointer
