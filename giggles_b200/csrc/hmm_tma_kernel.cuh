@@ -296,9 +296,12 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
             mbar_wait(&s_full[sb], ((seq + nred) / n_stages) & 1u);
             bs = reinterpret_cast<const float *>(smem_raw + L.off_stage + sb * stage_bytes);
         }
-        // ---- per-lane hoisted column quantities.  With g = G_b[a(R2)] of the output block, m = [a(R2) defined]:
+        // ---- per-lane hoisted column quantities.  With g = G_b[a(R2)] of the output block:
         //   forward : alpha = F[a(R1)] * ( (g*cA) * x + g * rowterm + g*cbase )
-        //   backward: beta  = [a(R1) defined] * ( (m*cA*gin) * (fk*x) + m * rowterm + m*cbase ),  weight w = beta * F*g
+        //   backward: beta  = (cA*gin) * (fk*x) + rowterm + cbase, weight of the side sums w = beta * F*g.
+        // The reference zeroes beta where an allele of the pair is missing at c-1 (src/genotypehmm.cpp:309); those
+        // states have emission 0 (F/G slot 0), so they reach neither the next backward step nor any posterior and
+        // the mask is not applied here (the value stays finite).
         const float totv = xs[RR + 2 * R];
         const float ctot = cC * totv;
         const float *fgi = m0->fg_self;
@@ -311,8 +314,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
             if (FWD) {
                 kx[v] = gout[v] * cA; kr[v] = gout[v]; kc[v] = gout[v] * cb;
             } else {
-                const float m = a2o[v] != 0 ? 1.f : 0.f;
-                kx[v] = m * cA * (weigh ? fgi[NCi + a2i[v]] : 1.f); kr[v] = m; kc[v] = m * cb;
+                kx[v] = cA * (weigh ? fgi[NCi + a2i[v]] : 1.f); kr[v] = 1.f; kc[v] = cb;
             }
             colacc[v] = 0.f;
         }
@@ -357,15 +359,14 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
                     colacc[v] += o[v];
                 }
             } else {
-                const bool rdef = a1ob != 0;
+                float dot = 0.f;
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    const float t = fmaf(kx[v], fk * x[v], fmaf(kr[v], rowterm, kc[v]));
-                    o[v] = rdef ? t : 0.f;
-                    const float fg = fo * gout[v];
-                    rs = fmaf(o[v], fg, rs);
-                    colacc[v] = fmaf(o[v], fg, colacc[v]);
+                    o[v] = fmaf(kx[v], fk * x[v], rowterm + kc[v]);
+                    dot = fmaf(o[v], gout[v], dot);
+                    colacc[v] = fmaf(fo, o[v], colacc[v]);      // times gout[v] once per block, below
                 }
+                rs = fo * dot;
             }
             if (rvalid && cok) *reinterpret_cast<float4 *>(ocol + rowb) = make_float4(o[0], o[1], o[2], o[3]);
             if (FWD) {
@@ -391,6 +392,10 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
         // ---- column sums across the row groups (double-buffered scratch: one barrier per item)
         float *cr = s_colred + parity_item * ngrp * Rp;
         float *tr = s_totred + parity_item * ngrp;
+        if (!FWD) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) colacc[v] *= gout[v];
+        }
         if (cok) *reinterpret_cast<float4 *>(cr + grp * Rp + ccol) = make_float4(colacc[0], colacc[1], colacc[2], colacc[3]);
         if (gl == 0) tr[grp] = totacc;
         consumer_bar();
