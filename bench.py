@@ -12,7 +12,7 @@ at the HBM roofline).  A step is one complete forward-backward over the window: 
 every forward column, every genotype posterior; with 256 columns the state does not fit HBM, so the
 checkpoint schedule (recompute) is part of the step, as it is at full scale.  Synthetic data, seeded.
 
-N > 1: every rank sweeps its own window (different seed, same shape) — chains are independent, there is
+N > 1: every rank sweeps its own copy of the window (independent chains of identical size) — there is
 no data-path collective ("weak" scaling); the end-to-end arm adds the final gather of posteriors to rank 0.
 """
 from __future__ import annotations
@@ -207,7 +207,7 @@ def main():
         except Exception as e:  # the baseline must never take the GPU number down with it
             cpu_baseline = {"value": None, "unit": UNIT, "cores": cores, "kind": "unavailable", "sample": str(e)}
 
-    problem = config2_window(args.columns, seed=2 + rank, max_coverage=args.max_coverage, n_haps=args.haps)
+    problem = config2_window(args.columns, seed=2, max_coverage=args.max_coverage, n_haps=args.haps)   # same shape AND size on every rank (weak scaling)
     cp = capi.CProblem(problem)
     h = capi.Hmm(cp, device=local_rank)
     st0 = h.stats()

@@ -81,7 +81,7 @@ class gg_stats(C.Structure):
 
 # every symbol include/giggles_b200.h declares (tests check that the library exports them all)
 SYMBOLS = [
-    "gg_hmm_run", "gg_hmm_create", "gg_hmm_sweep", "gg_hmm_fetch", "gg_hmm_stats", "gg_hmm_destroy", "gg_arena_release",
+    "gg_hmm_run", "gg_hmm_create", "gg_hmm_sweep", "gg_hmm_fetch", "gg_hmm_stats", "gg_hmm_destroy", "gg_arena_release", "gg_hmm_debug_scales",
     "gg_result_likelihoods", "gg_result_n_columns", "gg_result_flat", "gg_result_free", "gg_result_call", "gg_result_from_host",
     "gg_plan_build", "gg_plan_n_columns", "gg_plan_active", "gg_plan_untagged", "gg_plan_shared_mask_prev",
     "gg_plan_compatible_prev", "gg_plan_free",
@@ -109,6 +109,7 @@ def lib() -> C.CDLL:
     L.gg_hmm_sweep.argtypes = [vp, C.c_int] + errargs
     L.gg_hmm_fetch.argtypes = [vp, C.POINTER(vp)] + errargs
     L.gg_hmm_stats.argtypes = [vp, C.POINTER(gg_stats)]
+    L.gg_hmm_debug_scales.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
     L.gg_hmm_destroy.argtypes = [vp]
     L.gg_hmm_destroy.restype = None
     L.gg_result_likelihoods.argtypes = [vp, u32, C.POINTER(u32)]
@@ -258,6 +259,12 @@ class Hmm:
         out = C.c_void_p()
         _check(lib().gg_hmm_fetch(self._h, C.byref(out), err, len(err)), err)
         return Result(out)
+
+    def debug_scales(self):
+        n = self.cp.p.n_columns
+        a, b = np.zeros(n), np.zeros(n)
+        lib().gg_hmm_debug_scales(self._h, as_ptr(a, C.c_double), as_ptr(b, C.c_double))
+        return a, b
 
     def stats(self) -> dict:
         s = gg_stats()

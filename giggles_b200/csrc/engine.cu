@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -83,6 +84,11 @@ struct ArenaCache {
         }
         cudaFree(p);
         return nullptr;
+    }
+    size_t cached(int dev) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = slot.find(dev);
+        return it == slot.end() ? 0 : it->second.second;
     }
     void give(int dev, unsigned char *p, size_t n) {
         std::lock_guard<std::mutex> g(mu);
@@ -294,61 +300,82 @@ struct Engine {
         ++h->stats.n_launches;
     }
 
-    // Pipelined bulk-copy kernel (hmm_tma_kernel.cuh): fp32, R % 4 == 0, one block record per stage.
-    static const void *tma_kernel(bool fwd, uint32_t G) {
-        switch (G) {
-#define GG_TMA(GG) case GG: return fwd ? (const void *)step_tma_kernel<true, GG> : (const void *)step_tma_kernel<false, GG>;
-            GG_TMA(1) GG_TMA(2) GG_TMA(4) GG_TMA(8) GG_TMA(16) GG_TMA(32)
+    // Pipelined bulk-copy kernel (hmm_tma_kernel.cuh): fp32, R % 4 == 0, R <= 512.
+    static const void *tma_kernel(bool fwd, uint32_t G, int NS) {
+#define GG_TMA(GG, NN) if (G == GG && NS == NN) return fwd ? (const void *)step_tma_kernel<true, GG, NN> : (const void *)step_tma_kernel<false, GG, NN>;
+        GG_TMA(1, 1) GG_TMA(2, 1) GG_TMA(4, 1) GG_TMA(8, 1) GG_TMA(16, 1) GG_TMA(32, 1) GG_TMA(32, 2) GG_TMA(32, 4)
 #undef GG_TMA
-        }
         return nullptr;
     }
 
     static bool try_launch_tma(gg_hmm *h, const StepArgs<T> &a, const ColumnPlan &pco, bool fwd) {
         if (sizeof(T) != 4 || h->kernel_variant == 1 || a.in == nullptr) return false;
-        if (a.R % 4 != 0 || a.R > 128 || h->shape.V != 4 || h->shape.NS != 1) return false;
-        const uint32_t rpi = 32 / a.G, ngrp = kTmaConsumerWarps * rpi;
-        const uint32_t nred = fwd ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
-        const void *k = tma_kernel(fwd, a.G);
+        if (a.R % 4 != 0 || a.R > 512 || h->shape.V != 4) return false;
+        const int NS = h->shape.NS == 3 ? 4 : h->shape.NS;
+        const void *k = tma_kernel(fwd, a.G, NS);
         if (!k) return false;
         if (!h->tma_attr_done) {
             for (uint32_t g = 1; g <= 32; g <<= 1)
-                for (bool f : {false, true})
-                    GG_CUDA(cudaFuncSetAttribute(tma_kernel(f, g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
+                for (bool f : {false, true}) {
+                    GG_CUDA(cudaFuncSetAttribute(tma_kernel(f, g, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
+                    if (g == 32)
+                        for (int ns : {2, 4})
+                            GG_CUDA(cudaFuncSetAttribute(tma_kernel(f, g, ns), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
+                }
             h->tma_attr_done = true;
         }
-        // two CTAs per SM with 3-4 stages each when they fit (more warps to hide latency), else one with up to 8
-        auto fit = [&](uint32_t lo, uint32_t hi, size_t cap, uint32_t &stages, TmaSmemLayout &L) {
+        const uint32_t rpi = 32 / a.G;
+        const uint32_t nred = fwd ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
+        const uint32_t ncls = pco.n_alleles + 1;
+        // geometry search: most consumer warps first, then the largest row tile (<= ~40 KB) that leaves >= 3 stages;
+        // two CTAs per SM when a whole block is one tile and everything fits twice
+        struct Pick { uint32_t cw, tr, stages, ctas; TmaGeom L; bool ok; } pick{};
+        auto fit = [&](uint32_t cw, uint32_t tr, uint32_t lo, uint32_t hi, size_t cap, uint32_t &stages, TmaGeom &L) {
             for (stages = hi; stages >= lo; --stages) {
-                L = tma_smem_layout(a.R, a.BS, stages, ngrp, pco.n_alleles + 1, fwd, nred > 1);
+                L = tma_geom(a.R, tr, stages, cw * rpi, ncls, fwd, nred > 1);
                 if (L.total <= cap) return true;
             }
             return false;
         };
-        uint32_t stages = 0, ctas = 2;
-        TmaSmemLayout L{};
-        if (h->kernel_variant == 2 || !fit(3, 4, kMaxDynSmemTma2, stages, L)) {
-            ctas = 1;
-            if (!fit(3, kTmaMaxStages, kMaxDynSmemTma, stages, L)) return false;
+        if (a.R <= 128) {
+            uint32_t st; TmaGeom L;
+            if (h->kernel_variant != 2 && fit(8, a.R, 3, 4, kMaxDynSmemTma2, st, L)) pick = {8, a.R, st, 2, L, true};
+            else if (fit(8, a.R, 3, kTmaMaxStages, kMaxDynSmemTma, st, L)) pick = {8, a.R, st, 1, L, true};
         }
-        auto key = std::make_tuple(k, (int)kTmaThreads, (size_t)L.total);
+        if (!pick.ok) {
+            for (uint32_t cw : {8u, 4u, 2u}) {
+                if (NS == 1 && cw != 8) continue;     // the single-slot kernels are compiled for 8 consumer warps
+                const uint32_t ngrp = cw * rpi;
+                uint32_t tr_max = std::min<uint32_t>(a.R, (40u * 1024u) / (a.R * 4u));
+                tr_max = std::max<uint32_t>(ngrp, tr_max / ngrp * ngrp);
+                for (uint32_t tr = tr_max; tr >= ngrp && !pick.ok; tr -= ngrp) {
+                    uint32_t st; TmaGeom L;
+                    if (fit(cw, std::min<uint32_t>(tr, a.R), 3, 6, kMaxDynSmemTma, st, L)) pick = {cw, std::min<uint32_t>(tr, a.R), st, 1, L, true};
+                    if (tr == ngrp) break;
+                }
+                if (pick.ok) break;
+            }
+        }
+        if (!pick.ok) return false;
+        const int threads = 32 * (1 + (int)pick.cw);
+        auto key = std::make_tuple(k, threads, (size_t)pick.L.total);
         auto it = h->occ_cache.find(key);
         int occ;
         if (it == h->occ_cache.end()) {
-            GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kTmaThreads, L.total));
+            GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, pick.L.total));
             h->occ_cache[key] = occ;
         } else {
             occ = it->second;
         }
         if (occ < 1) return false;
-        ctas = std::min<uint32_t>(ctas, (uint32_t)occ);
+        const uint32_t ctas = std::min<uint32_t>(pick.ctas, (uint32_t)occ);
         const uint64_t n_items = (uint64_t)1 << pco.u;
         const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)h->num_sms * ctas);
         StepArgs<float> af;
         std::memcpy(&af, &a, sizeof(af));
-        uint32_t ns = stages;
-        void *params[] = {(void *)&af, (void *)&ns};
-        GG_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(kTmaThreads), params, L.total, h->stream));
+        uint32_t ns = pick.stages, tr = pick.tr;
+        void *params[] = {(void *)&af, (void *)&ns, (void *)&tr};
+        GG_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(threads), params, pick.L.total, h->stream));
         ++h->stats.n_launches;
         return true;
     }
@@ -424,7 +451,7 @@ struct Engine {
         if (budget == 0) {
             size_t free_b = 0, total_b = 0;
             GG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            budget = (uint64_t)(free_b * 0.8);
+            budget = (uint64_t)((free_b + g_arena_cache.cached(h->device)) * 0.8);   // the retired arena is ours to reuse
         }
         // if everything fits there is no reason to reserve more than that
         uint64_t all = 0;
@@ -446,6 +473,13 @@ struct Engine {
             GG_CUDA(cudaMalloc(&h->arena, h->sched.arena_bytes));
             h->arena_bytes = h->sched.arena_bytes;
         }
+        // test hook: GG_POISON_ARENA=1 fills the state arena with NaN bit patterns so that any read of a value the
+        // schedule has not produced yet shows up in the posteriors
+        if (const char *poison = std::getenv("GG_POISON_ARENA"))
+            if (poison[0] == '1' && h->arena) GG_CUDA(cudaMemsetAsync(h->arena, 0xFF, h->arena_bytes, h->stream));
+        GG_CUDA(cudaMemsetAsync(h->d_scale_a.p, 0, C * sizeof(double), h->stream));
+        GG_CUDA(cudaMemsetAsync(h->d_scale_b.p, 0, C * sizeof(double), h->stream));
+        if (pl.gl_offsets[C]) GG_CUDA(cudaMemsetAsync(h->d_result.p, 0, pl.gl_offsets[C] * sizeof(double), h->stream));
         GG_CUDA(cudaStreamSynchronize(h->stream));
         // stats that do not depend on a sweep
         gg_stats &st = h->stats;
@@ -622,6 +656,15 @@ void gg_hmm_destroy(gg_hmm *h) {
 }
 
 void gg_arena_release(void) { g_arena_cache.clear(); }
+
+int gg_hmm_debug_scales(gg_hmm *h, double *alpha_scale, double *beta_scale) {
+    if (!h) return GG_ERR_INVALID;
+    const size_t n = h->plan.n_columns * sizeof(double);
+    if (n == 0) return GG_OK;
+    if (cudaMemcpy(alpha_scale, h->d_scale_a.p, n, cudaMemcpyDeviceToHost) != cudaSuccess) return GG_ERR_CUDA;
+    if (cudaMemcpy(beta_scale, h->d_scale_b.p, n, cudaMemcpyDeviceToHost) != cudaSuccess) return GG_ERR_CUDA;
+    return GG_OK;
+}
 
 int gg_hmm_run(const gg_problem *p, const gg_options *o, gg_result **out, char *err, size_t errlen) {
     if (out) *out = nullptr;

@@ -1,59 +1,67 @@
 // Pipelined column step for sm_100a: bulk-async (TMA) staging of bipartition blocks.
 //
-// Same arithmetic as step_kernel (hmm_kernels.cuh) for fp32 columns with R % 4 == 0 whose block
-// record (R^2 + 2R + 4 floats) fits a shared-memory stage.  One persistent CTA per SM:
+// Same arithmetic as step_kernel (hmm_kernels.cuh) for fp32 columns with R % 4 == 0 (R <= 512).  Persistent CTAs:
 //
-//   warp 0      producer.  For every work item (one output bipartition block) it issues, per input
-//               block, ONE cp.async.bulk global->shared of the whole record (values + row/col/total
-//               sums) into the next free stage of a ring and, for the forward step, one more for the
-//               beta block of the posterior; the copy completes on the stage's "full" mbarrier.  It
-//               also fetches the item's F/G emission vectors into the stage's metadata.
-//   warps 1..8  consumers.  Wait on "full", run the row loop out of shared memory (LDS.128),
-//               store the produced block straight from registers (STG.128), hand the stage back
-//               through its "empty" mbarrier.
+//   warp 0      producer.  A work item is one output bipartition block; it is cut into TILES of TR consecutive
+//               rows (TR = R, one tile, while a whole block record fits a stage: R <= 128).  Per tile and per
+//               input block the producer issues ONE cp.async.bulk global->shared of the tile's rows into the next
+//               free stage of a ring (the first tile also brings the block's row/col/total sums, which sit right
+//               behind the values) and, for the forward step, one more for the beta rows of the posterior.  Copies
+//               complete on the stage's "full" mbarrier.  The item's F/G emission vectors are prefetched one item
+//               ahead and travel in the stage's metadata.
+//   warps 1..CW consumers.  Wait on "full", run the row loop out of shared memory (LDS.128), store the produced
+//               rows straight from registers (STG.128), hand the stage back through its "empty" mbarrier.
 //
-// With n stages of ~31 KB (R = 88) an SM keeps 4-6 records in flight, which is what hides HBM
-// latency; the generic kernel can only keep what its registers hold.
+// With 3-8 stages of 30-40 KB an SM keeps >100 KB of loads in flight, which is what hides HBM latency; the
+// register-staged generic kernel cannot.
 #pragma once
 #include "hmm_kernels.cuh"
 
 namespace gg {
 
 constexpr int kTmaMaxStages = 8;
-constexpr int kTmaConsumerWarps = 8;
-constexpr int kTmaThreads = 32 * (1 + kTmaConsumerWarps);
+constexpr int kTmaMaxConsumerWarps = 8;
 
 struct TmaStageMeta {
     uint32_t b_out, b_self, pad0, pad1;
-    float fg_out[2 * kMaxClasses + 2];    // F then G of the output block (k == 0 stage only)
+    float fg_out[2 * kMaxClasses + 2];    // F then G of the output block (first load of an item only)
     float fg_self[2 * kMaxClasses + 2];   // backward: F then G of the block held by this stage
 };
 
-struct TmaSmemLayout {
-    uint32_t off_stage, off_meta, off_acc, off_colred, off_totred, off_fgo, off_q, off_al_o, off_al_i, off_rord, off_rsum, total;
+// Geometry shared by host (sizes) and device (pointers).
+struct TmaGeom {
+    uint32_t TR, n_tiles, n_iter_t, TRp;          // rows per tile, tiles per block, row iterations per tile, padded rows
+    uint32_t side_off, stage_bytes;               // byte offset of the side record inside a stage
+    uint32_t off_stage, off_meta, off_acc, off_side, off_colred, off_totred, off_fgo, off_q, off_al_o, off_al_i,
+        off_rord, off_rsum, total;
 };
-__host__ __device__ inline TmaSmemLayout tma_smem_layout(uint32_t R, uint32_t BS, uint32_t n_stages, uint32_t ngrp,
-                                                         uint32_t ncls_out, bool fwd, bool need_acc) {
-    TmaSmemLayout L;
+__host__ __device__ inline TmaGeom tma_geom(uint32_t R, uint32_t TR, uint32_t n_stages, uint32_t ngrp, uint32_t ncls_out,
+                                            bool fwd, bool need_acc) {
+    TmaGeom g;
     const uint32_t Rp = (R + 3u) & ~3u;
-    const uint32_t stage_bytes = (BS * 4u + 127u) & ~127u;
+    g.TR = TR;
+    g.n_tiles = (R + TR - 1) / TR;
+    g.n_iter_t = (TR + ngrp - 1) / ngrp;
+    g.TRp = g.n_iter_t * ngrp;
+    g.side_off = TR * R * 4u;
+    g.stage_bytes = (g.side_off + (2u * R + 4u) * 4u + 127u) & ~127u;
     uint32_t o = 0;
-    L.off_stage = o; o += n_stages * stage_bytes;
-    L.off_meta = o; o += n_stages * (uint32_t)sizeof(TmaStageMeta);
+    g.off_stage = o; o += n_stages * g.stage_bytes;
+    g.off_meta = o; o += n_stages * (uint32_t)sizeof(TmaStageMeta);
     o = (o + 15u) & ~15u;
-    L.off_acc = o; o += need_acc ? stage_bytes : 0;
-    L.off_colred = o; o += 2 * ngrp * Rp * 4;          // double-buffered across items
-    L.off_totred = o; o += 2 * ngrp * 4;
-    L.off_fgo = o; o += 48 * 4;                          // item's F/G vector when stage 0 is released early
-    L.off_q = o; o += fwd ? ngrp * ncls_out * Rp * 4 : 0;
-    L.off_al_o = o; o += Rp;
-    L.off_al_i = o; o += Rp;
-    o = (o + 3u) & ~3u;
+    g.off_acc = o; o += need_acc ? g.side_off : 0;                       // reduce-set accumulator (one tile)
+    g.off_side = o; o += (need_acc || g.n_tiles > 1) ? (2u * Rp + 4u) * 4u : 0;   // block side sums kept across tiles
+    g.off_colred = o; o += 2 * ngrp * Rp * 4;                            // double-buffered across items
+    g.off_totred = o; o += 2 * ngrp * 4;
+    g.off_fgo = o; o += 48 * 4;
+    g.off_q = o; o += fwd ? ngrp * ncls_out * Rp * 4 : 0;
+    g.off_al_o = o; o += Rp;
+    g.off_al_i = o; o += Rp;
     o = (o + 7u) & ~7u;
-    L.off_rord = o; o += (Rp + ngrp) * 8;               // per-row metadata (2 words), padded to whole row iterations
-    L.off_rsum = o; o += 2 * Rp * 4;                    // row sums of the produced block, double-buffered across items
-    L.total = (o + 127u) & ~127u;
-    return L;
+    g.off_rord = o; o += g.n_tiles * g.TRp * 8;                          // per-row metadata (2 words)
+    g.off_rsum = o; o += 2 * Rp * 4;                                     // row sums of the produced block
+    g.total = (o + 127u) & ~127u;
+    return g;
 }
 
 // ---- mbarrier / bulk-copy PTX ------------------------------------------------------------------
@@ -78,18 +86,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kTmaConsumerWarps) : "memory"); }
+__device__ __forceinline__ void consumer_bar(uint32_t nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
-// row metadata, all pre-scaled to byte offsets so the row loop does no address arithmetic:
-//   x = byte offset of the row inside a block (R1*R*4) | valid << 31
-//   y = R1*4 | (allele class of R1 in the output column)*4 << 10 | (... in the input column)*4 << 20
-__device__ __forceinline__ uint2 pack_row(uint32_t R1, uint32_t R, uint32_t a1o, uint32_t a1i) {
-    return make_uint2((R1 * R * 4u) | 0x80000000u, (R1 * 4u) | (a1o * 4u) << 10 | (a1i * 4u) << 20);
+// row metadata, pre-scaled to byte offsets so the row loop does no address arithmetic:
+//   x = byte offset of the row inside its tile ((R1 - row0)*R*4) | valid << 31
+//   y = R1*4 (12 bits) | (allele class of R1 in the output column)*4 << 12 (7 bits) | (... input column)*4 << 19
+__device__ __forceinline__ uint2 pack_row(uint32_t R1, uint32_t row0, uint32_t R, uint32_t a1o, uint32_t a1i) {
+    return make_uint2(((R1 - row0) * R * 4u) | 0x80000000u, (R1 * 4u) | (a1o * 4u) << 12 | (a1i * 4u) << 19);
 }
 
-template <bool FWD, int G>
-__global__ void __launch_bounds__(kTmaThreads, 2)
-step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
+template <bool FWD, int G, int NS>
+__global__ void __launch_bounds__(32 * (1 + kTmaMaxConsumerWarps), (NS == 1 ? 2 : 1))
+step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t TR) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_full[kTmaMaxStages];
     __shared__ __align__(8) uint64_t s_empty[kTmaMaxStages];
@@ -100,24 +108,25 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
     const uint32_t R = a.R, BS = a.BS;
     const uint32_t RR = R * R;
     const uint32_t Rp = (R + 3u) & ~3u;
-    const uint32_t stage_bytes = (BS * 4u + 127u) & ~127u;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // consumer warps: always 8 for the single-slot kernels (compile-time row-group count), chosen by the host otherwise
+    const uint32_t CW = (NS == 1) ? (uint32_t)kTmaMaxConsumerWarps : (blockDim.x >> 5) - 1;
+    const uint32_t nct = 32 * CW;
     constexpr uint32_t rpi = 32u / G;
-    constexpr uint32_t ngrp = kTmaConsumerWarps * rpi;
+    const uint32_t ngrp = CW * rpi;
     const uint32_t NCo = a.nA_out + 1, NCi = a.nA_in + 1;
     const uint32_t fgs_o = 2 * NCo, fgs_i = 2 * NCi;
     const uint32_t nred = FWD ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
     const uint32_t n_bcast = FWD ? (a.u_out - a.n_sh) : a.n_free_left;
-    const uint32_t nload = nred + (FWD ? 1u : 0u);
-    const TmaSmemLayout L = tma_smem_layout(R, BS, n_stages, ngrp, NCo, FWD, nred > 1);
+    const uint32_t nload = nred + (FWD ? 1u : 0u);      // loads per tile
+    const TmaGeom L = tma_geom(R, TR, n_stages, ngrp, NCo, FWD, nred > 1);
     TmaStageMeta *s_meta = reinterpret_cast<TmaStageMeta *>(smem_raw + L.off_meta);
     const uint32_t n_items = 1u << a.u_out;
-    const uint32_t n_iter = (R + ngrp - 1) / ngrp;
 
     if (tid == 0) {
         for (uint32_t s = 0; s < n_stages; ++s) {
             mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], kTmaConsumerWarps);
+            mbar_init(&s_empty[s], CW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -126,26 +135,36 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
     uint8_t *s_al_i = smem_raw + L.off_al_i;
     uint2 *s_rowmeta = reinterpret_cast<uint2 *>(smem_raw + L.off_rord);
     float *s_q = reinterpret_cast<float *>(smem_raw + L.off_q);
-    for (uint32_t t = tid; t < n_iter * ngrp; t += blockDim.x) {
-        uint2 m = make_uint2(0u, 0u);   // padding rows: offset 0, class 0 (zero emission weight), not valid
-        if (t < R) {
-            const uint32_t R1 = (FWD && a.row_order) ? a.row_order[t] : t;
-            m = pack_row(R1, R, a.al_out[R1], a.al_in[R1]);
-        }
-        s_rowmeta[t] = m;
-    }
     for (uint32_t t = tid; t < R; t += blockDim.x) {
         s_al_o[t] = a.al_out[t];
         s_al_i[t] = a.al_in[t];
     }
+    for (uint32_t t = tid; t < L.n_tiles * L.TRp; t += blockDim.x) s_rowmeta[t] = make_uint2(0u, 0u);   // padding rows
     if (FWD)
         for (uint32_t t = tid; t < ngrp * NCo * Rp; t += blockDim.x) s_q[t] = 0.f;
+    __syncthreads();
+    // rows of a tile are visited in allele-class order (forward: the posterior accumulators are parked only when
+    // the class changes); one tile: the planner's sorted order; several tiles: a counting sort per tile
+    if (L.n_tiles == 1) {
+        for (uint32_t t = tid; t < R; t += blockDim.x) {
+            const uint32_t R1 = (FWD && a.row_order) ? a.row_order[t] : t;
+            s_rowmeta[t] = pack_row(R1, 0, R, s_al_o[R1], s_al_i[R1]);
+        }
+    } else if (tid < L.n_tiles) {
+        const uint32_t row0 = tid * TR, row1 = min(R, row0 + TR);
+        uint32_t pos = tid * L.TRp;
+        if (FWD) {
+            for (uint32_t cls = 0; cls < NCo; ++cls)
+                for (uint32_t r = row0; r < row1; ++r)
+                    if (s_al_o[r] == cls) s_rowmeta[pos++] = pack_row(r, row0, R, cls, s_al_i[r]);
+        } else {
+            for (uint32_t r = row0; r < row1; ++r) s_rowmeta[pos++] = pack_row(r, row0, R, s_al_o[r], s_al_i[r]);
+        }
+    }
     __syncthreads();
 
     if (warp == 0) {
         // =========================== producer ===========================
-        // F/G vectors are prefetched one item ahead so that their global-load latency never sits between two
-        // bulk copies.
         auto decode = [&](uint32_t item, uint32_t &b_out, uint32_t &b_in0) {
             const uint32_t lo = item & ((1u << n_bcast) - 1u), sh = item >> n_bcast;
             if (FWD) {
@@ -159,7 +178,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
         uint32_t seq = 0;
         uint32_t nb_out = 0, nb_in0 = 0;
         float pf_o0 = 0.f, pf_o1 = 0.f, pf_i0 = 0.f, pf_i1 = 0.f;
-        auto prefetch = [&](uint32_t item) {
+        auto prefetch = [&](uint32_t item) {      // F/G vectors one item ahead: their latency never sits between copies
             uint32_t bo = 0, bi = 0;
             if (lane == 0) decode(item, bo, bi);
             nb_out = __shfl_sync(0xffffffffu, bo, 0);
@@ -176,38 +195,49 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
             const uint32_t b_out = nb_out, b_in0 = nb_in0;
             const float fo0 = pf_o0, fo1 = pf_o1, fi0 = pf_i0, fi1 = pf_i1;
             if (item + gridDim.x < n_items) prefetch(item + gridDim.x);
-            uint32_t subm = 0;
-            for (uint32_t j = 0; j < nload; ++j, ++seq) {
-                const uint32_t s = seq % n_stages;
-                const uint32_t par = ((seq / n_stages) & 1u) ^ 1u;
-                const bool is_beta = FWD && (j == nred);
-                const uint32_t bk = is_beta ? b_out : (FWD ? (b_in0 | subm) : (b_in0 | (j << a.n_sh)));
-                subm = (subm - a.free_mask) & a.free_mask;
-                if (lane == 0) mbar_wait(&s_empty[s], par);
-                __syncwarp();
-                TmaStageMeta *m = &s_meta[s];
-                if (lane == 0) {
-                    const float *src = (is_beta ? a.beta : a.in) + (uint64_t)bk * BS;
-                    const uint32_t bytes = is_beta ? RR * 4u : BS * 4u;
-                    mbar_expect_tx(&s_full[s], bytes);
-                    bulk_g2s(smem_raw + L.off_stage + s * stage_bytes, src, bytes, &s_full[s]);
-                    m->b_out = b_out;
-                    m->b_self = bk;
-                }
-                if (j == 0) {
-                    if (lane < fgs_o) m->fg_out[lane] = fo0;
-                    if (lane + 32 < fgs_o) m->fg_out[lane + 32] = fo1;
-                }
-                if (!FWD) {
-                    if (j == 0) {
-                        if (lane < fgs_i) m->fg_self[lane] = fi0;
-                        if (lane + 32 < fgs_i) m->fg_self[lane + 32] = fi1;
-                    } else {
-                        for (uint32_t t = lane; t < fgs_i; t += 32) m->fg_self[t] = a.fg_in[(uint64_t)bk * fgs_i + t];
+            for (uint32_t t = 0; t < L.n_tiles; ++t) {
+                const uint32_t row0 = t * TR, rows = min(TR, R - row0);
+                uint32_t subm = 0;
+                for (uint32_t j = 0; j < nload; ++j, ++seq) {
+                    const uint32_t s = seq % n_stages;
+                    const uint32_t par = ((seq / n_stages) & 1u) ^ 1u;
+                    const bool is_beta = FWD && (j == nred);
+                    const uint32_t bk = is_beta ? b_out : (FWD ? (b_in0 | subm) : (b_in0 | (j << a.n_sh)));
+                    subm = (subm - a.free_mask) & a.free_mask;
+                    if (lane == 0) mbar_wait(&s_empty[s], par);
+                    __syncwarp();
+                    TmaStageMeta *m = &s_meta[s];
+                    if (lane == 0) {
+                        unsigned char *dst = smem_raw + L.off_stage + s * L.stage_bytes;
+                        const float *blk = (is_beta ? a.beta : a.in) + (uint64_t)bk * BS;
+                        const uint32_t row_bytes = rows * R * 4u, side_bytes = (2u * R + 4u) * 4u;
+                        const bool side = !is_beta && t == 0;
+                        if (side && L.n_tiles == 1) {           // values and side record are contiguous: one copy
+                            mbar_expect_tx(&s_full[s], row_bytes + side_bytes);
+                            bulk_g2s(dst, blk, row_bytes + side_bytes, &s_full[s]);
+                        } else {
+                            mbar_expect_tx(&s_full[s], row_bytes + (side ? side_bytes : 0u));
+                            bulk_g2s(dst, blk + (uint64_t)row0 * R, row_bytes, &s_full[s]);
+                            if (side) bulk_g2s(dst + L.side_off, blk + RR, side_bytes, &s_full[s]);
+                        }
+                        m->b_out = b_out;
+                        m->b_self = bk;
                     }
+                    if (j == 0 && t == 0) {
+                        if (lane < fgs_o) m->fg_out[lane] = fo0;
+                        if (lane + 32 < fgs_o) m->fg_out[lane + 32] = fo1;
+                    }
+                    if (!FWD) {
+                        if (j == 0) {
+                            if (lane < fgs_i) m->fg_self[lane] = fi0;
+                            if (lane + 32 < fgs_i) m->fg_self[lane + 32] = fi1;
+                        } else {
+                            for (uint32_t q = lane; q < fgs_i; q += 32) m->fg_self[q] = a.fg_in[(uint64_t)bk * fgs_i + q];
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_full[s]);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_full[s]);
             }
         }
         return;
@@ -218,197 +248,241 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
     const uint32_t sub = lane / G, gl = lane % G;
     const uint32_t grp = cwarp * rpi + sub;
     float *s_acc = reinterpret_cast<float *>(smem_raw + L.off_acc);
+    float *s_side = reinterpret_cast<float *>(smem_raw + L.off_side);
     float *s_colred = reinterpret_cast<float *>(smem_raw + L.off_colred);
     float *s_totred = reinterpret_cast<float *>(smem_raw + L.off_totred);
     float *s_fgo = reinterpret_cast<float *>(smem_raw + L.off_fgo);
     float *s_rsum = reinterpret_cast<float *>(smem_raw + L.off_rsum);
+    const bool multi = L.n_tiles > 1;
 
     const float inv = (float)(1.0 / *a.in_scale);
     const float cA = (float)a.tA * inv, cB = (float)a.tB * inv, cC = (float)a.tC * inv;
-    const bool cok = gl * 4 < R;
-    const uint32_t ccol = cok ? gl * 4 : 0u;       // idle lanes shadow columns 0..3 with zero weight, stores off
-    uint32_t a2o[4], a2i[4];
+    // this lane's columns: NS groups of 4; idle slots shadow columns 0..3 with zero weight and no stores
+    bool cok[NS];
+    uint32_t ccol[NS];
+    uint32_t a2o[NS][4], a2i[NS][4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        a2o[v] = cok ? s_al_o[ccol + v] : 0u;
-        a2i[v] = cok ? s_al_i[ccol + v] : 0u;
+    for (int s = 0; s < NS; ++s) {
+        cok[s] = (s * G + gl) * 4 < R;
+        ccol[s] = cok[s] ? (s * G + gl) * 4 : 0u;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            a2o[s][v] = cok[s] ? s_al_o[ccol[s] + v] : 0u;
+            a2i[s][v] = cok[s] ? s_al_i[ccol[s] + v] : 0u;
+        }
     }
-    float qc[4] = {0.f, 0.f, 0.f, 0.f};
+    float qc[NS][4];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) qc[s][v] = 0.f;
     uint32_t cur_cls = 0xffffffffu;
     float cta_sum = 0.f, sacc = 0.f;
     uint32_t seq = 0, parity_item = 0;
 
-    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, parity_item ^= 1u) {
-        const uint32_t s0 = seq % n_stages;
-        mbar_wait(&s_full[s0], (seq / n_stages) & 1u);
-        const TmaStageMeta *m0 = &s_meta[s0];
-        const uint32_t b_out = m0->b_out;
-        const float *xs = reinterpret_cast<const float *>(smem_raw + L.off_stage + s0 * stage_bytes);
-        const float *fgo = m0->fg_out;
-        bool pre_weighted = false;
-        if (nred > 1) {
-            // fold the reduce set into s_acc; every thread owns the same elements for all k
-            for (uint32_t k = 0; k < nred; ++k) {
-                const uint32_t sk = (seq + k) % n_stages;
-                if (k > 0) mbar_wait(&s_full[sk], ((seq + k) / n_stages) & 1u);
-                const float *st = reinterpret_cast<const float *>(smem_raw + L.off_stage + sk * stage_bytes);
-                const float *fgk = s_meta[sk].fg_self;
-                for (uint32_t it = 0; it < n_iter; ++it) {
-                    const uint32_t ridx = it * ngrp + grp;
-                    if (ridx < R && cok) {
-                        float4 v = *reinterpret_cast<const float4 *>(st + ridx * R + ccol);
-                        if (!FWD) {
-                            const float fk = fgk[s_al_i[ridx]];
-                            v.x *= fk * fgk[NCi + a2i[0]];
-                            v.y *= fk * fgk[NCi + a2i[1]];
-                            v.z *= fk * fgk[NCi + a2i[2]];
-                            v.w *= fk * fgk[NCi + a2i[3]];
-                        }
-                        float4 *dst = reinterpret_cast<float4 *>(s_acc + ridx * R + ccol);
-                        if (k > 0) {
-                            const float4 o = *dst;
-                            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                        }
-                        *dst = v;
-                    }
-                }
-                // side sums: row/col/total records sit behind the values
-                for (uint32_t t = ctid; t < 2 * R + 1; t += 32 * kTmaConsumerWarps) {
-                    const float v = st[RR + t];
-                    s_acc[RR + t] = (k > 0 ? s_acc[RR + t] : 0.f) + v;
-                }
-                // stage 0 also carries the item's F/G vector: keep a copy, then every stage can go back at once
-                // (the reduce set may be longer than the ring, so nothing may be held across it)
-                if (k == 0)
-                    for (uint32_t t = ctid; t < fgs_o; t += 32 * kTmaConsumerWarps) s_fgo[t] = m0->fg_out[t];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[sk]);
-            }
-            consumer_bar();   // side sums and the F/G copy were written by other threads
-            fgo = s_fgo;
-            xs = s_acc;
-            pre_weighted = true;
-        }
-        const float *bs = xs;
-        uint32_t sb = 0;
-        if (FWD) {
-            sb = (seq + nred) % n_stages;
-            mbar_wait(&s_full[sb], ((seq + nred) / n_stages) & 1u);
-            bs = reinterpret_cast<const float *>(smem_raw + L.off_stage + sb * stage_bytes);
-        }
-        // ---- per-lane hoisted column quantities.  With g = G_b[a(R2)] of the output block:
-        //   forward : alpha = F[a(R1)] * ( (g*cA) * x + g * rowterm + g*cbase )
-        //   backward: beta  = (cA*gin) * (fk*x) + rowterm + cbase, weight of the side sums w = beta * F*g.
-        // The reference zeroes beta where an allele of the pair is missing at c-1 (src/genotypehmm.cpp:309); those
-        // states have emission 0 (F/G slot 0), so they reach neither the next backward step nor any posterior and
-        // the mask is not applied here (the value stays finite).
-        const float totv = xs[RR + 2 * R];
-        const float ctot = cC * totv;
-        const float *fgi = m0->fg_self;
-        const bool weigh = !FWD && !pre_weighted;
-        float kx[4], kr[4], kc[4], gout[4], colacc[4];
+    auto park_q = [&]() {     // posterior accumulators of the finished row class -> this group's private slot
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const float cb = cB * xs[RR + R + ccol + v] + ctot;
-            gout[v] = fgo[NCo + a2o[v]];
-            if (FWD) {
-                kx[v] = gout[v] * cA; kr[v] = gout[v]; kc[v] = gout[v] * cb;
-            } else {
-                kx[v] = cA * (weigh ? fgi[NCi + a2i[v]] : 1.f); kr[v] = 1.f; kc[v] = cb;
+        for (int s = 0; s < NS; ++s)
+            if (cok[s]) {
+                float4 *qd = reinterpret_cast<float4 *>(s_q + (grp * NCo + (cur_cls >> 2)) * Rp + ccol[s]);
+                float4 o = *qd;
+                o.x += qc[s][0]; o.y += qc[s][1]; o.z += qc[s][2]; o.w += qc[s][3];
+                *qd = o;
+                qc[s][0] = qc[s][1] = qc[s][2] = qc[s][3] = 0.f;
             }
-            colacc[v] = 0.f;
-        }
-        float totacc = 0.f;
-        float *outp = a.out + (uint64_t)b_out * BS;
-        const char *xcol = reinterpret_cast<const char *>(xs + ccol);
-        const char *bcol = reinterpret_cast<const char *>(bs + ccol);
-        const char *xrow = reinterpret_cast<const char *>(xs + RR);
-        const char *fgo_b = reinterpret_cast<const char *>(fgo);
-        const char *fgi_b = reinterpret_cast<const char *>(fgi);
-        char *ocol = reinterpret_cast<char *>(outp + ccol);
+    };
+
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, parity_item ^= 1u) {
+        float kx[NS][4], kr[NS][4], kc[NS][4], gout[NS][4], colacc[NS][4];
+        float totacc = 0.f, totv = 0.f;
+        const float *fgo = nullptr, *fgi = nullptr;
+        float *outp = nullptr;
+        bool weigh = false;
         float *rsum = s_rsum + parity_item * Rp;
 
-#pragma unroll 4
-        for (uint32_t it = 0; it < n_iter; ++it) {
-            const uint2 meta = s_rowmeta[it * ngrp + grp];
-            const uint32_t rowb = meta.x & 0x7fffffffu;
-            const uint32_t r1b = meta.y & 0x3ffu, a1ob = (meta.y >> 10) & 0x3ffu, a1ib = (meta.y >> 20) & 0x3ffu;
-            const bool rvalid = (int32_t)meta.x < 0;
-            const float4 xv = *reinterpret_cast<const float4 *>(xcol + rowb);
-            const float rowterm = cB * *reinterpret_cast<const float *>(xrow + r1b);
-            const float fo = *reinterpret_cast<const float *>(fgo_b + a1ob);
-            const float fk = weigh ? *reinterpret_cast<const float *>(fgi_b + a1ib) : 1.f;
-            if (FWD && a1ob != cur_cls) {         // row class changed: park the posterior accumulators
-                if (cur_cls != 0xffffffffu && cok) {   // idle lanes must not touch the slot of the lane they shadow
-                    float4 *qd = reinterpret_cast<float4 *>(s_q + (grp * NCo + (cur_cls >> 2)) * Rp + ccol);
-                    float4 o = *qd;
-                    o.x += qc[0]; o.y += qc[1]; o.z += qc[2]; o.w += qc[3];
-                    *qd = o;
-                    qc[0] = qc[1] = qc[2] = qc[3] = 0.f;
+        for (uint32_t t = 0; t < L.n_tiles; ++t) {
+            const uint32_t row0 = t * TR, rows = min(TR, R - row0);
+            const uint32_t s0 = seq % n_stages;
+            mbar_wait(&s_full[s0], (seq / n_stages) & 1u);
+            const TmaStageMeta *m0 = &s_meta[s0];
+            const uint32_t b_out = m0->b_out;     // read before the stage can go back to the producer
+            const float *xs = reinterpret_cast<const float *>(smem_raw + L.off_stage + s0 * L.stage_bytes);
+            const float *side = reinterpret_cast<const float *>(smem_raw + L.off_stage + s0 * L.stage_bytes + L.side_off);
+            bool early_release = false;
+            if (nred > 1) {
+                // fold the reduce set into s_acc (and, on the first tile, the side records into s_side); every thread
+                // owns the same elements for all k.  Nothing is held across the loop: the set may exceed the ring.
+                for (uint32_t k = 0; k < nred; ++k) {
+                    const uint32_t sk = (seq + k) % n_stages;
+                    if (k > 0) mbar_wait(&s_full[sk], ((seq + k) / n_stages) & 1u);
+                    const unsigned char *stb = smem_raw + L.off_stage + sk * L.stage_bytes;
+                    const float *st = reinterpret_cast<const float *>(stb);
+                    const float *fgk = s_meta[sk].fg_self;
+                    for (uint32_t it = 0; it < L.n_iter_t; ++it) {
+                        const uint32_t rl = it * ngrp + grp;     // row inside the tile, natural order
+                        if (rl < rows) {
+                            const float fk = FWD ? 1.f : fgk[s_al_i[row0 + rl]];
+#pragma unroll
+                            for (int s = 0; s < NS; ++s)
+                                if (cok[s]) {
+                                    float4 v = *reinterpret_cast<const float4 *>(st + rl * R + ccol[s]);
+                                    if (!FWD) {
+                                        v.x *= fk * fgk[NCi + a2i[s][0]];
+                                        v.y *= fk * fgk[NCi + a2i[s][1]];
+                                        v.z *= fk * fgk[NCi + a2i[s][2]];
+                                        v.w *= fk * fgk[NCi + a2i[s][3]];
+                                    }
+                                    float4 *dst = reinterpret_cast<float4 *>(s_acc + rl * R + ccol[s]);
+                                    if (k > 0) {
+                                        const float4 o = *dst;
+                                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                                    }
+                                    *dst = v;
+                                }
+                        }
+                    }
+                    if (t == 0) {
+                        const float *sd = reinterpret_cast<const float *>(stb + L.side_off);
+                        for (uint32_t q = ctid; q < 2 * R + 1; q += nct) s_side[q] = (k > 0 ? s_side[q] : 0.f) + sd[q];
+                        if (k == 0)
+                            for (uint32_t q = ctid; q < fgs_o; q += nct) s_fgo[q] = m0->fg_out[q];
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_empty[sk]);
                 }
-                cur_cls = a1ob;
+                consumer_bar(nct);
+                xs = s_acc;
+                early_release = true;
+            } else if (multi && t == 0) {
+                // one input block, several tiles: keep its side record and F/G vector for the later tiles
+                for (uint32_t q = ctid; q < 2 * R + 1; q += nct) s_side[q] = side[q];
+                for (uint32_t q = ctid; q < fgs_o; q += nct) s_fgo[q] = m0->fg_out[q];
+                consumer_bar(nct);
             }
-            const float x[4] = {xv.x, xv.y, xv.z, xv.w};
-            float o[4];
-            float rs = 0.f;
+            if (nred > 1 || multi) side = s_side;
+            const float *bs = xs;
+            uint32_t sb = 0;
             if (FWD) {
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    o[v] = fo * fmaf(kx[v], x[v], fmaf(kr[v], rowterm, kc[v]));
-                    rs += o[v];
-                    colacc[v] += o[v];
-                }
-            } else {
-                float dot = 0.f;
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    o[v] = fmaf(kx[v], fk * x[v], rowterm + kc[v]);
-                    dot = fmaf(o[v], gout[v], dot);
-                    colacc[v] = fmaf(fo, o[v], colacc[v]);      // times gout[v] once per block, below
-                }
-                rs = fo * dot;
+                sb = (seq + nred) % n_stages;
+                mbar_wait(&s_full[sb], ((seq + nred) / n_stages) & 1u);
+                bs = reinterpret_cast<const float *>(smem_raw + L.off_stage + sb * L.stage_bytes);
             }
-            if (rvalid && cok) *reinterpret_cast<float4 *>(ocol + rowb) = make_float4(o[0], o[1], o[2], o[3]);
-            if (FWD) {
-                const float4 bv = *reinterpret_cast<const float4 *>(bcol + rowb);
-                qc[0] = fmaf(o[0], bv.x, qc[0]); qc[1] = fmaf(o[1], bv.y, qc[1]);
-                qc[2] = fmaf(o[2], bv.z, qc[2]); qc[3] = fmaf(o[3], bv.w, qc[3]);
-            }
+            if (t == 0) {
+                // ---- per-lane hoisted column quantities.  With g = G_b[a(R2)] of the output block:
+                //   forward : alpha = F[a(R1)] * ( (g*cA) * x + g * rowterm + g*cbase )
+                //   backward: beta  = (cA*gin) * (fk*x) + rowterm + cbase, weight of the side sums w = beta * F*g.
+                // The reference zeroes beta where an allele of the pair is missing at c-1 (src/genotypehmm.cpp:309);
+                // those states have emission 0 (F/G slot 0), so they reach neither the next backward step nor any
+                // posterior and the mask is not applied here (the value stays finite).
+                fgo = (nred > 1 || multi) ? s_fgo : m0->fg_out;
+                weigh = !FWD && nred == 1;
+                totv = side[2 * R];
+                const float ctot = cC * totv;
+                outp = a.out + (uint64_t)b_out * BS;
 #pragma unroll
-            for (int sh = G >> 1; sh > 0; sh >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, sh);
-            if (gl == 0 && rvalid) *reinterpret_cast<float *>(reinterpret_cast<char *>(rsum) + r1b) = rs;
-            totacc += rs;        // identical in every lane of the row group; padding rows contribute 0
+                for (int s = 0; s < NS; ++s)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float cb = cB * side[R + ccol[s] + v] + ctot;
+                        gout[s][v] = fgo[NCo + a2o[s][v]];
+                        if (FWD) {
+                            kx[s][v] = gout[s][v] * cA; kr[s][v] = gout[s][v]; kc[s][v] = gout[s][v] * cb;
+                        } else {
+                            kx[s][v] = cA * (weigh ? m0->fg_self[NCi + a2i[s][v]] : 1.f); kr[s][v] = 1.f; kc[s][v] = cb;
+                        }
+                        colacc[s][v] = 0.f;
+                    }
+            }
+            fgi = s_meta[s0].fg_self;     // backward, nred == 1: F of the (single) input block, valid for this tile's stage
+            const char *xrow = reinterpret_cast<const char *>(side);
+            const char *fgo_b = reinterpret_cast<const char *>(fgo);
+            const char *fgi_b = reinterpret_cast<const char *>(fgi);
+            const char *xtile = reinterpret_cast<const char *>(xs);
+            const char *btile = reinterpret_cast<const char *>(bs);
+            char *otile = reinterpret_cast<char *>(outp + (uint64_t)row0 * R);
+            const uint2 *meta_t = s_rowmeta + t * L.TRp + grp;
+
+#pragma unroll (NS == 1 ? 4 : 2)
+            for (uint32_t it = 0; it < L.n_iter_t; ++it) {
+                const uint2 meta = meta_t[it * ngrp];
+                const uint32_t rowb = meta.x & 0x7fffffffu;
+                const uint32_t r1b = meta.y & 0xfffu, a1ob = (meta.y >> 12) & 0x7fu, a1ib = (meta.y >> 19) & 0x7fu;
+                const bool rvalid = (int32_t)meta.x < 0;
+                const float rowterm = cB * *reinterpret_cast<const float *>(xrow + r1b);
+                const float fo = *reinterpret_cast<const float *>(fgo_b + a1ob);
+                const float fk = weigh ? *reinterpret_cast<const float *>(fgi_b + a1ib) : 1.f;
+                if (FWD && a1ob != cur_cls) {         // row class changed: park the posterior accumulators
+                    if (cur_cls != 0xffffffffu) park_q();
+                    cur_cls = a1ob;
+                }
+                float rs = 0.f;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const float4 xv = *reinterpret_cast<const float4 *>(xtile + rowb + ccol[s] * 4);
+                    const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+                    float o[4];
+                    if (FWD) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            o[v] = fo * fmaf(kx[s][v], x[v], fmaf(kr[s][v], rowterm, kc[s][v]));
+                            rs += o[v];
+                            colacc[s][v] += o[v];
+                        }
+                    } else {
+                        float dot = 0.f;
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            o[v] = fmaf(kx[s][v], fk * x[v], rowterm + kc[s][v]);
+                            dot = fmaf(o[v], gout[s][v], dot);
+                            colacc[s][v] = fmaf(fo, o[v], colacc[s][v]);      // times gout once per block, below
+                        }
+                        rs = fmaf(fo, dot, rs);
+                    }
+                    if (rvalid && cok[s]) *reinterpret_cast<float4 *>(otile + rowb + ccol[s] * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (FWD) {
+                        const float4 bv = *reinterpret_cast<const float4 *>(btile + rowb + ccol[s] * 4);
+                        qc[s][0] = fmaf(o[0], bv.x, qc[s][0]); qc[s][1] = fmaf(o[1], bv.y, qc[s][1]);
+                        qc[s][2] = fmaf(o[2], bv.z, qc[s][2]); qc[s][3] = fmaf(o[3], bv.w, qc[s][3]);
+                    }
+                }
+#pragma unroll
+                for (int sh = G >> 1; sh > 0; sh >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, sh);
+                if (gl == 0 && rvalid) *reinterpret_cast<float *>(reinterpret_cast<char *>(rsum) + r1b) = rs;
+                totacc += rs;        // identical in every lane of the row group; padding rows contribute 0
+            }
+            // ---- hand the stages back
+            __syncwarp();
+            if (lane == 0) {
+                if (!early_release) mbar_arrive(&s_empty[s0]);
+                if (FWD) mbar_arrive(&s_empty[sb]);
+            }
+            seq += nload;
+            if (nred > 1 && t + 1 < L.n_tiles) consumer_bar(nct);   // s_acc is rewritten by the next tile
         }
         // backward: the column scale.  Without missing alleles sum(beta_{c-1}[b']) equals the reduced input total
         // exactly (tA + 2R tB + R^2 tC = 1); any positive scalar of that magnitude serves, so use it.
-        if (!FWD && ctid == 32 * kTmaConsumerWarps - 1) sacc += totv;
-        // ---- hand the stages back
-        __syncwarp();
-        if (lane == 0) {
-            if (nred == 1) mbar_arrive(&s_empty[s0]);
-            if (FWD) mbar_arrive(&s_empty[sb]);
-        }
-        seq += nload;
+        if (!FWD && ctid == nct - 1) sacc += totv;
         // ---- column sums across the row groups (double-buffered scratch: one barrier per item)
         float *cr = s_colred + parity_item * ngrp * Rp;
         float *tr = s_totred + parity_item * ngrp;
-        if (!FWD) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) colacc[v] *= gout[v];
+        for (int s = 0; s < NS; ++s) {
+            if (!FWD) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) colacc[s][v] *= gout[s][v];
+            }
+            if (cok[s]) *reinterpret_cast<float4 *>(cr + grp * Rp + ccol[s]) = make_float4(colacc[s][0], colacc[s][1], colacc[s][2], colacc[s][3]);
         }
-        if (cok) *reinterpret_cast<float4 *>(cr + grp * Rp + ccol) = make_float4(colacc[0], colacc[1], colacc[2], colacc[3]);
         if (gl == 0) tr[grp] = totacc;
-        consumer_bar();
-        for (uint32_t t = ctid; t < R; t += 32 * kTmaConsumerWarps) {
+        consumer_bar(nct);
+        for (uint32_t q = ctid; q < R; q += nct) {
             float cs = 0.f;
-#pragma unroll 8
-            for (uint32_t g = 0; g < ngrp; ++g) cs += cr[g * Rp + t];
-            outp[RR + R + t] = cs;
-            outp[RR + t] = rsum[t];
+            for (uint32_t g = 0; g < ngrp; ++g) cs += cr[g * Rp + q];
+            outp[RR + R + q] = cs;
+            outp[RR + q] = rsum[q];
         }
-        if (ctid == 32 * kTmaConsumerWarps - 1) {
+        if (ctid == nct - 1) {
             float ts = 0.f;
-#pragma unroll 8
             for (uint32_t g = 0; g < ngrp; ++g) ts += tr[g];
             outp[RR + 2 * R] = ts;
             cta_sum += ts;
@@ -417,22 +491,16 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
 
     // ---- kernel epilogue (consumer threads only)
     float *mypart = a.partial + (uint64_t)blockIdx.x * kPartialStride;
-    const uint32_t nct = 32 * kTmaConsumerWarps;
     if (FWD) {
-        if (cur_cls != 0xffffffffu && cok) {
-            float4 *qd = reinterpret_cast<float4 *>(s_q + (grp * NCo + (cur_cls >> 2)) * Rp + ccol);
-            float4 o = *qd;
-            o.x += qc[0]; o.y += qc[1]; o.z += qc[2]; o.w += qc[3];
-            *qd = o;
-        }
-        consumer_bar();
+        if (cur_cls != 0xffffffffu) park_q();
+        consumer_bar(nct);
         for (uint32_t idx = ctid; idx < NCo * R; idx += nct) {
             const uint32_t cls = idx / R, t = idx % R;
             float v = 0.f;
             for (uint32_t g = 0; g < ngrp; ++g) v += s_q[(g * NCo + cls) * Rp + t];
             s_q[cls * Rp + t] = v;
         }
-        consumer_bar();
+        consumer_bar(nct);
         for (uint32_t p = ctid; p < NCo * NCo; p += nct) {
             const uint32_t i = p / NCo, j = p % NCo;
             float w = 0.f;
@@ -445,12 +513,12 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
     }
     if (ctid == nct - 1) mypart[kMaxClasses * kMaxClasses] = cta_sum;
     __threadfence();
-    consumer_bar();
+    consumer_bar(nct);
     if (ctid == 0) {
         const unsigned int ticket = atomicAdd(a.counter, 1u);
         s_last = (ticket == gridDim.x - 1);
     }
-    consumer_bar();
+    consumer_bar(nct);
     if (!s_last) return;
     __threadfence();
     const uint32_t npair = FWD ? NCo * NCo : 0u;
@@ -460,7 +528,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages) {
         for (uint32_t blk = 0; blk < gridDim.x; ++blk) acc += (double)__ldcg(a.partial + (uint64_t)blk * kPartialStride + slot);
         s_W[slot] = acc;
     }
-    consumer_bar();
+    consumer_bar(nct);
     if (ctid == 0) {
         *a.out_scale = s_W[kMaxClasses * kMaxClasses];
         *a.counter = 0u;

@@ -120,6 +120,8 @@ void gg_hmm_destroy(gg_hmm *h);
 /* gg_hmm_destroy keeps the state arena of the last handle per device for the next gg_hmm_create / gg_hmm_run
  * (allocating >100 GB costs more than sweeping a small chromosome); this frees it. */
 void gg_arena_release(void);
+/* test hook: the per-column sums of the stored (unnormalised) alpha / beta columns of the last sweep, [n_columns] each */
+int gg_hmm_debug_scales(gg_hmm *h, double *alpha_scale, double *beta_scale);
 
 /* ---- result access: replaces GenotypeHMM::get_genotype_likelihoods
  *      (src/genotypehmm.cpp:563-574, giggles/core.pyx:505-506).  Returns a pointer

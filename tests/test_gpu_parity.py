@@ -174,6 +174,44 @@ def test_full_size_properties(max_cov):
     assert done
 
 
+def test_config4_shape_2pow20_bipartitions():
+    # configs[3]: max-coverage 20 => 2^20 bipartition blocks per column (small panel so that fp64 fits beside it)
+    from giggles_b200.synth import config4_window
+    p = config4_window(n_columns=6, n_haps=12, max_coverage=20)
+    assert int(p.untagged_per_column().max()) == 20
+    r32 = capi.hmm_run(p, device=0)
+    r64 = capi.hmm_run(p, device=0, precision=1)
+    assert_posteriors_close(r32.values, r64.values)
+    off = p.gl_offsets()
+    sums = np.add.reduceat(r32.values, off[:-1].astype(np.int64))
+    assert np.abs(sums - 1.0).max() < 1e-12
+
+
+def test_config5_shape_400_haplotypes_multiallelic():
+    # configs[4]: 400-haplotype panel (160,000 ordered pairs), 3..16 alleles at every site
+    from giggles_b200.synth import config5_window
+    p = config5_window(n_columns=6, n_haps=400, max_coverage=3)
+    want = oracle.oracle_run(p)
+    assert_posteriors_close(capi.hmm_run(p, device=0).values, want)
+    assert np.abs(capi.hmm_run(p, device=0, precision=1).values - want).max() <= 1e-11
+
+
+def test_config1_shape_full_coverage_slice():
+    # configs[0]: R = 10, 10x HiFi; a slice at the config's own density and coverage cap
+    from giggles_b200.synth import config1
+    p = config1(n_columns=150)
+    want = oracle.oracle_run(p)
+    r = capi.hmm_run(p, device=0)
+    assert_posteriors_close(r.values, want)
+    calls = r.call(0.0)
+    off = p.gl_offsets()
+    for c in range(p.n_columns):
+        l = want[off[c]:off[c + 1]].tolist()
+        srt = sorted(l)
+        if abs(srt[-1] - srt[-2]) >= 1e-5:
+            assert calls.gt_index[c] == py_determine_genotype(l)
+
+
 def test_read_relabelling_symmetry_full_size():
     # swapping the two sides of EVERY read and transposing nothing else must leave genotype posteriors of
     # bi-allelic columns unchanged (the model is symmetric under (b,R1,R2) <-> (~b,R2,R1))

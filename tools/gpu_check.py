@@ -24,6 +24,10 @@ cases = [
     dict(n_columns=30, n_haps=64, coverage=8, max_coverage=6, read_len_mean=900, multiallelic_frac=0.5, max_alleles=16),
     dict(n_columns=30, n_haps=128, coverage=6, max_coverage=4, read_len_mean=900, tags="mixed"),
     dict(n_columns=30, n_haps=88, coverage=10, max_coverage=7, read_len_mean=600, missing_frac=0.05),
+    dict(n_columns=10, n_haps=400, coverage=6, max_coverage=3, read_len_mean=700, multiallelic_frac=1.0, max_alleles=16, window=True),
+    dict(n_columns=12, n_haps=256, coverage=8, max_coverage=4, read_len_mean=500, tags="mixed", multiallelic_frac=0.3),
+    dict(n_columns=12, n_haps=132, coverage=8, max_coverage=4, read_len_mean=500, missing_frac=0.03),
+    dict(n_columns=8, n_haps=512, coverage=4, max_coverage=2, read_len_mean=600),
 ]
 worst = 0.0
 for i, kw in enumerate(cases):
@@ -45,6 +49,8 @@ for i, kw in enumerate(cases):
               f"maxerr={err.max():.3e} nan={bad} at={int(err.argmax())} {dt*1e3:.1f} ms")
         if tag == "BAD":
             off = p.gl_offsets()
+            nanc = [c for c in range(p.n_columns) if np.isnan(got[off[c]:off[c+1]]).any()]
+            print("   NaN columns:", nanc[:50], "of", p.n_columns)
             c = int(np.searchsorted(off, err.argmax(), side='right') - 1)
             print("   first bad column", c, "got", got[off[c]:off[c+1]], "want", want[off[c]:off[c+1]])
 # budget variations must give bit-identical results

@@ -6,8 +6,8 @@ import numpy as np
 from giggles_b200 import capi
 from giggles_b200.synth import config2_window, config1
 
-def run(name, p, budget=0, reps=3):
-    t = time.time(); h = capi.Hmm(p, device=0, budget=budget); tc = time.time() - t
+def run(name, p, budget=0, reps=3, kv=0):
+    t = time.time(); h = capi.Hmm(p, device=0, budget=budget, kernel_variant=kv); tc = time.time() - t
     st = h.stats()
     for _ in range(2): h.sweep()
     best = 1e9
@@ -27,6 +27,11 @@ if "small" in which:
 if "mid" in which:
     run("cfg2 mc=10 C=64", config2_window(64, max_coverage=10))
     run("cfg2 mc=12 C=64", config2_window(64, max_coverage=12))
+if "r400" in which:
+    from giggles_b200.synth import config5_window
+    run("cfg5 R=400 mc=6 C=24", config5_window(24, max_coverage=6))
+    run("cfg5 R=400 mc=6 C=24 generic", config5_window(24, max_coverage=6), kv=1)
+    run("R=256 biallelic mc=8 C=24", config2_window(24, max_coverage=8, n_haps=256))
 if "big" in which:
     run("cfg2 mc=15 C=48", config2_window(48, max_coverage=15))
     run("cfg2 mc=15 C=160 (checkpointed)", config2_window(160, max_coverage=15), reps=1)
