@@ -15,7 +15,7 @@ import numpy as np
 from .problem import Problem, as_ptr
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgiggles_b200.so")
+LIB_PATH = os.environ.get("GG_LIB", os.path.join(_HERE, "libgiggles_b200.so"))   # GG_LIB: A/B runs of two builds
 
 GG_OK, GG_ERR_INVALID, GG_ERR_NO_DEVICE, GG_ERR_CUDA, GG_ERR_NOMEM, GG_ERR_UNSUPPORTED = range(6)
 GG_MAX_ALLELES = 16
@@ -109,7 +109,8 @@ def lib() -> C.CDLL:
     L.gg_hmm_sweep.argtypes = [vp, C.c_int] + errargs
     L.gg_hmm_fetch.argtypes = [vp, C.POINTER(vp)] + errargs
     L.gg_hmm_stats.argtypes = [vp, C.POINTER(gg_stats)]
-    L.gg_hmm_debug_scales.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
+    if hasattr(L, "gg_hmm_debug_scales"):
+        L.gg_hmm_debug_scales.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
     L.gg_hmm_destroy.argtypes = [vp]
     L.gg_hmm_destroy.restype = None
     L.gg_result_likelihoods.argtypes = [vp, u32, C.POINTER(u32)]

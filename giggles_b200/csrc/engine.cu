@@ -120,7 +120,7 @@ struct gg_hmm {
     Plan plan;
     Schedule sched;
     bool fp64 = false;
-    int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined kernel with one CTA per SM
+    int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined, never two CTAs per SM, 3 = pipelined, never 16 consumer warps
     bool tma_attr_done = false;
     int device = 0;
     int num_sms = 0;
@@ -301,9 +301,11 @@ struct Engine {
     }
 
     // Pipelined bulk-copy kernel (hmm_tma_kernel.cuh): fp32, R % 4 == 0, R <= 512.
-    static const void *tma_kernel(bool fwd, uint32_t G, int NS) {
-#define GG_TMA(GG, NN) if (G == GG && NS == NN) return fwd ? (const void *)step_tma_kernel<true, GG, NN> : (const void *)step_tma_kernel<false, GG, NN>;
-        GG_TMA(1, 1) GG_TMA(2, 1) GG_TMA(4, 1) GG_TMA(8, 1) GG_TMA(16, 1) GG_TMA(32, 1) GG_TMA(32, 2) GG_TMA(32, 4)
+    static const void *tma_kernel(bool fwd, uint32_t G, int NS, bool mt, int cwt) {
+#define GG_TMA(GG, NN, MM, CC) if (G == GG && NS == NN && mt == MM && cwt == CC) return fwd ? (const void *)step_tma_kernel<true, GG, NN, MM, CC> : (const void *)step_tma_kernel<false, GG, NN, MM, CC>;
+        GG_TMA(1, 1, false, 8) GG_TMA(2, 1, false, 8) GG_TMA(4, 1, false, 8) GG_TMA(8, 1, false, 8) GG_TMA(16, 1, false, 8)
+        GG_TMA(32, 1, false, 8) GG_TMA(32, 1, false, 16)
+        GG_TMA(32, 1, true, 0) GG_TMA(32, 2, true, 0) GG_TMA(32, 4, true, 0)
 #undef GG_TMA
         return nullptr;
     }
@@ -311,25 +313,26 @@ struct Engine {
     static bool try_launch_tma(gg_hmm *h, const StepArgs<T> &a, const ColumnPlan &pco, bool fwd) {
         if (sizeof(T) != 4 || h->kernel_variant == 1 || a.in == nullptr) return false;
         if (a.R % 4 != 0 || a.R > 512 || h->shape.V != 4) return false;
-        const int NS = h->shape.NS == 3 ? 4 : h->shape.NS;
-        const void *k = tma_kernel(fwd, a.G, NS);
-        if (!k) return false;
+        const int NS = h->shape.NS;
         if (!h->tma_attr_done) {
             for (uint32_t g = 1; g <= 32; g <<= 1)
                 for (bool f : {false, true}) {
-                    GG_CUDA(cudaFuncSetAttribute(tma_kernel(f, g, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
-                    if (g == 32)
-                        for (int ns : {2, 4})
-                            GG_CUDA(cudaFuncSetAttribute(tma_kernel(f, g, ns), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
+                    GG_CUDA(cudaFuncSetAttribute(tma_kernel(f, g, 1, false, 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
+                    if (g == 32) {
+                        GG_CUDA(cudaFuncSetAttribute(tma_kernel(f, g, 1, false, 16), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
+                        for (int ns : {1, 2, 4})
+                            GG_CUDA(cudaFuncSetAttribute(tma_kernel(f, g, ns, true, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
+                    }
                 }
             h->tma_attr_done = true;
         }
         const uint32_t rpi = 32 / a.G;
         const uint32_t nred = fwd ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
         const uint32_t ncls = pco.n_alleles + 1;
-        // geometry search: most consumer warps first, then the largest row tile (<= ~40 KB) that leaves >= 3 stages;
-        // two CTAs per SM when a whole block is one tile and everything fits twice
-        struct Pick { uint32_t cw, tr, stages, ctas; TmaGeom L; bool ok; } pick{};
+        // geometry search.  Whole block = one tile (R <= 128): two CTAs of 8 consumer warps per SM when the column's
+        // footprint fits twice, else one CTA of 16 (same warp count, deeper ring), else one of 8.  Larger R: row tiles
+        // of <= ~40 KB, most consumer warps first, >= 3 stages.
+        struct Pick { uint32_t cw, tr, stages, ctas; int cwt; TmaGeom L; bool ok; } pick{};
         auto fit = [&](uint32_t cw, uint32_t tr, uint32_t lo, uint32_t hi, size_t cap, uint32_t &stages, TmaGeom &L) {
             for (stages = hi; stages >= lo; --stages) {
                 L = tma_geom(a.R, tr, stages, cw * rpi, ncls, fwd, nred > 1);
@@ -337,26 +340,29 @@ struct Engine {
             }
             return false;
         };
-        if (a.R <= 128) {
+        if (a.R <= 128 && NS == 1) {
             uint32_t st; TmaGeom L;
-            if (h->kernel_variant != 2 && fit(8, a.R, 3, 4, kMaxDynSmemTma2, st, L)) pick = {8, a.R, st, 2, L, true};
-            else if (fit(8, a.R, 3, kTmaMaxStages, kMaxDynSmemTma, st, L)) pick = {8, a.R, st, 1, L, true};
+            if (h->kernel_variant != 2 && fit(8, a.R, 3, 4, kMaxDynSmemTma2, st, L)) pick = {8, a.R, st, 2, 8, L, true};
+            else if (a.G == 32 && h->kernel_variant != 3 && fit(16, a.R, 3, kTmaMaxStages, kMaxDynSmemTma, st, L)) pick = {16, a.R, st, 1, 16, L, true};
+            else if (fit(8, a.R, 3, kTmaMaxStages, kMaxDynSmemTma, st, L)) pick = {8, a.R, st, 1, 8, L, true};
         }
-        if (!pick.ok) {
+        if (!pick.ok && a.G == 32) {
             for (uint32_t cw : {8u, 4u, 2u}) {
-                if (NS == 1 && cw != 8) continue;     // the single-slot kernels are compiled for 8 consumer warps
                 const uint32_t ngrp = cw * rpi;
                 uint32_t tr_max = std::min<uint32_t>(a.R, (40u * 1024u) / (a.R * 4u));
                 tr_max = std::max<uint32_t>(ngrp, tr_max / ngrp * ngrp);
                 for (uint32_t tr = tr_max; tr >= ngrp && !pick.ok; tr -= ngrp) {
                     uint32_t st; TmaGeom L;
-                    if (fit(cw, std::min<uint32_t>(tr, a.R), 3, 6, kMaxDynSmemTma, st, L)) pick = {cw, std::min<uint32_t>(tr, a.R), st, 1, L, true};
+                    const uint32_t trc = std::min<uint32_t>(tr, a.R);
+                    if (trc < a.R && fit(cw, trc, 3, 6, kMaxDynSmemTma, st, L)) pick = {cw, trc, st, 1, 0, L, true};
                     if (tr == ngrp) break;
                 }
                 if (pick.ok) break;
             }
         }
         if (!pick.ok) return false;
+        const void *k = tma_kernel(fwd, a.G, NS, pick.cwt == 0, pick.cwt);
+        if (!k) return false;
         const int threads = 32 * (1 + (int)pick.cw);
         auto key = std::make_tuple(k, threads, (size_t)pick.L.total);
         auto it = h->occ_cache.find(key);

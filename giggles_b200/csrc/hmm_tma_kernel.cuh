@@ -95,9 +95,12 @@ __device__ __forceinline__ uint2 pack_row(uint32_t R1, uint32_t row0, uint32_t R
     return make_uint2(((R1 - row0) * R * 4u) | 0x80000000u, (R1 * 4u) | (a1o * 4u) << 12 | (a1i * 4u) << 19);
 }
 
-template <bool FWD, int G, int NS>
-__global__ void __launch_bounds__(32 * (1 + kTmaMaxConsumerWarps), (NS == 1 ? 2 : 1))
-step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t TR) {
+// MT = false: a block is one tile (TR == R), known at compile time so the tile loop and its bookkeeping vanish.
+// CWT: consumer warps at compile time (8: two CTAs per SM; 16: one CTA per SM when the shared-memory footprint of a
+// column - reduce-set accumulator, many allele classes - does not fit twice); 0 = taken from blockDim.
+template <bool FWD, int G, int NS, bool MT, int CWT>
+__global__ void __launch_bounds__(32 * (1 + (CWT ? CWT : kTmaMaxConsumerWarps)), (CWT == 8 ? 2 : 1))
+step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t TR_arg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_full[kTmaMaxStages];
     __shared__ __align__(8) uint64_t s_empty[kTmaMaxStages];
@@ -108,9 +111,10 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
     const uint32_t R = a.R, BS = a.BS;
     const uint32_t RR = R * R;
     const uint32_t Rp = (R + 3u) & ~3u;
+    const uint32_t TR = MT ? TR_arg : R;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    // consumer warps: always 8 for the single-slot kernels (compile-time row-group count), chosen by the host otherwise
-    const uint32_t CW = (NS == 1) ? (uint32_t)kTmaMaxConsumerWarps : (blockDim.x >> 5) - 1;
+    // consumer warps
+    const uint32_t CW = CWT ? (uint32_t)CWT : (blockDim.x >> 5) - 1;
     const uint32_t nct = 32 * CW;
     constexpr uint32_t rpi = 32u / G;
     const uint32_t ngrp = CW * rpi;
@@ -120,6 +124,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
     const uint32_t n_bcast = FWD ? (a.u_out - a.n_sh) : a.n_free_left;
     const uint32_t nload = nred + (FWD ? 1u : 0u);      // loads per tile
     const TmaGeom L = tma_geom(R, TR, n_stages, ngrp, NCo, FWD, nred > 1);
+    const uint32_t n_tiles = MT ? L.n_tiles : 1u;
     TmaStageMeta *s_meta = reinterpret_cast<TmaStageMeta *>(smem_raw + L.off_meta);
     const uint32_t n_items = 1u << a.u_out;
 
@@ -139,18 +144,18 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
         s_al_o[t] = a.al_out[t];
         s_al_i[t] = a.al_in[t];
     }
-    for (uint32_t t = tid; t < L.n_tiles * L.TRp; t += blockDim.x) s_rowmeta[t] = make_uint2(0u, 0u);   // padding rows
+    for (uint32_t t = tid; t < n_tiles * L.TRp; t += blockDim.x) s_rowmeta[t] = make_uint2(0u, 0u);   // padding rows
     if (FWD)
         for (uint32_t t = tid; t < ngrp * NCo * Rp; t += blockDim.x) s_q[t] = 0.f;
     __syncthreads();
     // rows of a tile are visited in allele-class order (forward: the posterior accumulators are parked only when
     // the class changes); one tile: the planner's sorted order; several tiles: a counting sort per tile
-    if (L.n_tiles == 1) {
+    if (n_tiles == 1) {
         for (uint32_t t = tid; t < R; t += blockDim.x) {
             const uint32_t R1 = (FWD && a.row_order) ? a.row_order[t] : t;
             s_rowmeta[t] = pack_row(R1, 0, R, s_al_o[R1], s_al_i[R1]);
         }
-    } else if (tid < L.n_tiles) {
+    } else if (tid < n_tiles) {
         const uint32_t row0 = tid * TR, row1 = min(R, row0 + TR);
         uint32_t pos = tid * L.TRp;
         if (FWD) {
@@ -195,7 +200,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
             const uint32_t b_out = nb_out, b_in0 = nb_in0;
             const float fo0 = pf_o0, fo1 = pf_o1, fi0 = pf_i0, fi1 = pf_i1;
             if (item + gridDim.x < n_items) prefetch(item + gridDim.x);
-            for (uint32_t t = 0; t < L.n_tiles; ++t) {
+            for (uint32_t t = 0; t < n_tiles; ++t) {
                 const uint32_t row0 = t * TR, rows = min(TR, R - row0);
                 uint32_t subm = 0;
                 for (uint32_t j = 0; j < nload; ++j, ++seq) {
@@ -212,7 +217,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                         const float *blk = (is_beta ? a.beta : a.in) + (uint64_t)bk * BS;
                         const uint32_t row_bytes = rows * R * 4u, side_bytes = (2u * R + 4u) * 4u;
                         const bool side = !is_beta && t == 0;
-                        if (side && L.n_tiles == 1) {           // values and side record are contiguous: one copy
+                        if (side && n_tiles == 1) {           // values and side record are contiguous: one copy
                             mbar_expect_tx(&s_full[s], row_bytes + side_bytes);
                             bulk_g2s(dst, blk, row_bytes + side_bytes, &s_full[s]);
                         } else {
@@ -253,7 +258,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
     float *s_totred = reinterpret_cast<float *>(smem_raw + L.off_totred);
     float *s_fgo = reinterpret_cast<float *>(smem_raw + L.off_fgo);
     float *s_rsum = reinterpret_cast<float *>(smem_raw + L.off_rsum);
-    const bool multi = L.n_tiles > 1;
+    const bool multi = n_tiles > 1;
 
     const float inv = (float)(1.0 / *a.in_scale);
     const float cA = (float)a.tA * inv, cB = (float)a.tB * inv, cC = (float)a.tC * inv;
@@ -300,7 +305,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
         bool weigh = false;
         float *rsum = s_rsum + parity_item * Rp;
 
-        for (uint32_t t = 0; t < L.n_tiles; ++t) {
+        for (uint32_t t = 0; t < n_tiles; ++t) {
             const uint32_t row0 = t * TR, rows = min(TR, R - row0);
             const uint32_t s0 = seq % n_stages;
             mbar_wait(&s_full[s0], (seq / n_stages) & 1u);
@@ -397,12 +402,17 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
             const char *xrow = reinterpret_cast<const char *>(side);
             const char *fgo_b = reinterpret_cast<const char *>(fgo);
             const char *fgi_b = reinterpret_cast<const char *>(fgi);
-            const char *xtile = reinterpret_cast<const char *>(xs);
-            const char *btile = reinterpret_cast<const char *>(bs);
-            char *otile = reinterpret_cast<char *>(outp + (uint64_t)row0 * R);
+            const char *xcolp[NS], *bcolp[NS];
+            char *ocolp[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {      // per-lane column pointers: the row loop only adds the row offset
+                xcolp[s] = reinterpret_cast<const char *>(xs + ccol[s]);
+                bcolp[s] = reinterpret_cast<const char *>(bs + ccol[s]);
+                ocolp[s] = reinterpret_cast<char *>(outp + (uint64_t)row0 * R + ccol[s]);
+            }
             const uint2 *meta_t = s_rowmeta + t * L.TRp + grp;
 
-#pragma unroll (NS == 1 ? 4 : 2)
+#pragma unroll (NS == 1 ? (CWT == 16 ? 3 : 4) : 2)
             for (uint32_t it = 0; it < L.n_iter_t; ++it) {
                 const uint2 meta = meta_t[it * ngrp];
                 const uint32_t rowb = meta.x & 0x7fffffffu;
@@ -418,7 +428,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                 float rs = 0.f;
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
-                    const float4 xv = *reinterpret_cast<const float4 *>(xtile + rowb + ccol[s] * 4);
+                    const float4 xv = *reinterpret_cast<const float4 *>(xcolp[s] + rowb);
                     const float x[4] = {xv.x, xv.y, xv.z, xv.w};
                     float o[4];
                     if (FWD) {
@@ -438,9 +448,9 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                         }
                         rs = fmaf(fo, dot, rs);
                     }
-                    if (rvalid && cok[s]) *reinterpret_cast<float4 *>(otile + rowb + ccol[s] * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (rvalid && cok[s]) *reinterpret_cast<float4 *>(ocolp[s] + rowb) = make_float4(o[0], o[1], o[2], o[3]);
                     if (FWD) {
-                        const float4 bv = *reinterpret_cast<const float4 *>(btile + rowb + ccol[s] * 4);
+                        const float4 bv = *reinterpret_cast<const float4 *>(bcolp[s] + rowb);
                         qc[s][0] = fmaf(o[0], bv.x, qc[s][0]); qc[s][1] = fmaf(o[1], bv.y, qc[s][1]);
                         qc[s][2] = fmaf(o[2], bv.z, qc[s][2]); qc[s][3] = fmaf(o[3], bv.w, qc[s][3]);
                     }
@@ -457,7 +467,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                 if (FWD) mbar_arrive(&s_empty[sb]);
             }
             seq += nload;
-            if (nred > 1 && t + 1 < L.n_tiles) consumer_bar(nct);   // s_acc is rewritten by the next tile
+            if (nred > 1 && t + 1 < n_tiles) consumer_bar(nct);   // s_acc is rewritten by the next tile
         }
         // backward: the column scale.  Without missing alleles sum(beta_{c-1}[b']) equals the reduced input total
         // exactly (tA + 2R tB + R^2 tC = 1); any positive scalar of that magnitude serves, so use it.
