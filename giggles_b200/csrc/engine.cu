@@ -21,6 +21,7 @@
 #include "../../include/giggles_b200.h"
 #include "hmm_kernels.cuh"
 #include "hmm_tma_kernel.cuh"
+#include "hmm_chain_kernel.cuh"
 #include "plan.hpp"
 #include "result.hpp"
 #include "schedule.hpp"
@@ -121,7 +122,7 @@ struct gg_hmm {
     Schedule sched;
     bool fp64 = false;
     int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined, never two CTAs per SM, 3 = pipelined, never 16 consumer warps
-    bool tma_attr_done = false;
+    bool tma_attr_done = false, chain_attr_done = false;
     int device = 0;
     int num_sms = 0;
     size_t elem = 4;
@@ -135,6 +136,12 @@ struct gg_hmm {
     unsigned char *arena = nullptr;
     size_t arena_bytes = 0;
     DevBuf<unsigned int> d_counter;
+    // runs of consecutive single-block columns fused into one chain-kernel launch each
+    struct Run { bool fwd; uint32_t first, n, max_classes; uint64_t in_off; int64_t in_col; };
+    std::vector<Run> runs;
+    std::vector<ChainStep> chain_steps;
+    DevBuf<ChainStep> d_chain_steps;
+    std::vector<Op> exec_ops;   // the schedule after fusion (what gg_hmm_sweep replays)
     uint32_t max_grid = 0;
     LaunchShape shape{};
     std::map<std::tuple<const void *, int, size_t>, int> occ_cache;
@@ -405,6 +412,106 @@ struct Engine {
         }
     }
 
+    // ---- chain kernel (hmm_chain_kernel.cuh): fuse consecutive steps over columns without untagged reads
+    static const void *chain_kernel_ptr(bool fwd, uint32_t nit) {
+        switch (nit) {
+#define GG_CH(NN) case NN: return fwd ? (const void *)chain_kernel<true, NN> : (const void *)chain_kernel<false, NN>;
+            GG_CH(1) GG_CH(2) GG_CH(3) GG_CH(4) GG_CH(5) GG_CH(6) GG_CH(7) GG_CH(8)
+#undef GG_CH
+        }
+        return nullptr;
+    }
+
+    static void fuse_runs(gg_hmm *h) {
+        const Plan &pl = h->plan;
+        const uint32_t R = pl.n_haps;
+        const std::vector<Op> &ops = h->sched.ops;
+        h->exec_ops.clear();
+        h->runs.clear();
+        h->chain_steps.clear();
+        const bool eligible = sizeof(T) == 4 && h->kernel_variant != 1 && h->kernel_variant != 4 && R % 4 == 0 && R <= 128;
+        auto single = [&](uint32_t c) { return pl.cols[c].u == 0; };
+        auto op_ok = [&](const Op &op) {
+            if (!eligible) return false;
+            if (op.kind == OP_BWD) return single(op.c) && single(op.c + 1);
+            if (op.kind == OP_BWD_INIT) return single(op.c);
+            if (op.kind == OP_FWD) return single(op.c) && (op.c == 0 || single(op.c - 1));
+            return false;
+        };
+        size_t i = 0;
+        while (i < ops.size()) {
+            if (!op_ok(ops[i])) { h->exec_ops.push_back(ops[i++]); continue; }
+            const bool fwd = ops[i].kind == OP_FWD;
+            size_t j = i;
+            while (j < ops.size() && op_ok(ops[j]) && (ops[j].kind == OP_FWD) == fwd &&
+                   (j == i || (fwd ? ops[j].c == ops[j - 1].c + 1 : (ops[j].c + 1 == ops[j - 1].c && ops[j].in_off == ops[j - 1].out_off))))
+                ++j;
+            if (j - i < 4) { for (; i < j; ++i) h->exec_ops.push_back(ops[i]); continue; }
+            gg_hmm::Run run{};
+            run.fwd = fwd;
+            run.first = (uint32_t)h->chain_steps.size();
+            run.n = (uint32_t)(j - i);
+            run.in_col = -1;
+            for (size_t q = i; q < j; ++q) {
+                const Op &op = ops[q];
+                const ColumnPlan &pco = pl.cols[op.c];
+                ChainStep st{};
+                st.out_off = op.out_off;
+                st.beta_off = op.beta_off;
+                st.fg_out_off = op.fg_out_off;
+                st.fg_in_off = op.fg_in_off;
+                st.gl_off = pco.gl_off;
+                st.c_out = op.c;
+                st.nA_out = pco.n_alleles;
+                st.c_in = 0xffffffffu;
+                st.nA_in = 1;
+                const ColumnPlan *pt = nullptr;      // whose transition
+                if (fwd && op.c > 0) { st.c_in = op.c - 1; pt = &pco; }
+                if (op.kind == OP_BWD) { st.c_in = op.c + 1; pt = &pl.cols[op.c + 1]; }
+                if (st.c_in != 0xffffffffu) st.nA_in = pl.cols[st.c_in].n_alleles;
+                if (pt) { st.tA = (float)pt->tA; st.tB = (float)pt->tB; st.tC = (float)pt->tC; }
+                run.max_classes = std::max(run.max_classes, pco.n_alleles + 1);
+                if (q == i && st.c_in != 0xffffffffu) { run.in_off = op.in_off; run.in_col = st.c_in; }
+                h->chain_steps.push_back(st);
+            }
+            Op fused{};
+            fused.kind = OP_RUN;
+            fused.c = (uint32_t)h->runs.size();
+            h->runs.push_back(run);
+            h->exec_ops.push_back(fused);
+            i = j;
+        }
+        if (!h->chain_steps.empty()) h->d_chain_steps.upload(h->chain_steps, h->stream);
+    }
+
+    static void launch_run(gg_hmm *h, const Op &op) {
+        const gg_hmm::Run &run = h->runs[op.c];
+        const uint32_t R = h->plan.n_haps;
+        ChainArgs a{};
+        a.arena = h->arena;
+        a.steps = h->d_chain_steps.p + run.first;
+        a.n_steps = run.n;
+        a.in = run.in_col >= 0 ? reinterpret_cast<const float *>(h->arena + run.in_off) : nullptr;
+        a.in_scale = run.in_col >= 0 ? (run.fwd ? h->d_scale_a.p : h->d_scale_b.p) + run.in_col : nullptr;
+        a.scale = run.fwd ? h->d_scale_a.p : h->d_scale_b.p;
+        a.result = h->d_result.p;
+        a.allele1 = h->d_allele1.p;
+        a.R = R;
+        a.BS = (uint32_t)block_stride(R);
+        a.max_classes = run.max_classes;
+        const void *k = chain_kernel_ptr(run.fwd, (R + kChainWarps - 1) / kChainWarps);
+        const uint32_t smem = chain_smem_bytes(R, run.max_classes, run.fwd);
+        if (!h->chain_attr_done) {
+            for (uint32_t n = 1; n <= (uint32_t)kChainMaxNIT; ++n)
+                for (bool f : {false, true})
+                    GG_CUDA(cudaFuncSetAttribute(chain_kernel_ptr(f, n), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
+            h->chain_attr_done = true;
+        }
+        void *params[] = {(void *)&a};
+        GG_CUDA(cudaLaunchKernel(k, dim3(1), dim3(kChainThreads), params, smem, h->stream));
+        ++h->stats.n_launches;
+    }
+
     static void set_attrs() {
         static bool done = false;   // per process and per T
         if (done) return;
@@ -474,6 +581,7 @@ struct Engine {
             const std::string m = e.what();
             throw CudaError(m.find("budget") != std::string::npos ? GG_ERR_NOMEM : GG_ERR_INVALID, m);
         }
+        fuse_runs(h);
         h->arena = g_arena_cache.take(h->device, h->sched.arena_bytes, h->arena_bytes);
         if (!h->arena && h->sched.arena_bytes) {
             GG_CUDA(cudaMalloc(&h->arena, h->sched.arena_bytes));
@@ -510,7 +618,8 @@ struct Engine {
     static void sweep(gg_hmm *h, int timed) {
         gg_stats &st = h->stats;
         st.n_launches = 0;
-        const size_t nops = h->sched.ops.size();
+        const std::vector<Op> &ops = h->exec_ops;
+        const size_t nops = ops.size();
         const bool per_kernel = timed != 0;
         if (h->ev.size() < 2) {
             h->ev.resize(2);
@@ -524,13 +633,14 @@ struct Engine {
         }
         GG_CUDA(cudaEventRecord(h->ev[0], h->stream));
         for (size_t i = 0; i < nops; ++i) {
-            const Op &op = h->sched.ops[i];
+            const Op &op = ops[i];
             if (per_kernel) GG_CUDA(cudaEventRecord(h->ev[2 + 2 * i], h->stream));
             switch (op.kind) {
             case OP_EMIT: launch_emit(h, op); break;
             case OP_BWD_INIT: launch_step(h, op, false, true); break;
             case OP_BWD: launch_step(h, op, false, false); break;
             case OP_FWD: launch_step(h, op, true, false); break;
+            case OP_RUN: launch_run(h, op); break;
             }
             if (per_kernel) GG_CUDA(cudaEventRecord(h->ev[3 + 2 * i], h->stream));
         }
@@ -543,9 +653,10 @@ struct Engine {
             for (size_t i = 0; i < nops; ++i) {
                 float ms = 0.f;
                 GG_CUDA(cudaEventElapsedTime(&ms, h->ev[2 + 2 * i], h->ev[3 + 2 * i]));
-                switch (h->sched.ops[i].kind) {
+                switch (ops[i].kind) {
                 case OP_EMIT: st.last_emit_ms += ms; break;
                 case OP_FWD: st.last_fwd_ms += ms; break;
+                case OP_RUN: (h->runs[ops[i].c].fwd ? st.last_fwd_ms : st.last_bwd_ms) += ms; break;
                 default: st.last_bwd_ms += ms; break;
                 }
             }

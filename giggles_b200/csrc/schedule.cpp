@@ -211,6 +211,8 @@ void validate_schedule(const std::vector<uint64_t> &colb, const std::vector<uint
     uint32_t next_fwd = 0;
     for (const Op &o : s.ops) {
         switch (o.kind) {
+        case OP_RUN:
+            break;   // engine-side fusion happens after validation
         case OP_EMIT:
             for (uint32_t c = o.c; c <= o.hi; ++c) write(o.out_off + (pfg[c] - pfg[o.c]), fgb[c], tag(3, c));
             break;

@@ -15,7 +15,8 @@
 
 namespace gg {
 
-enum OpKind : uint8_t { OP_EMIT = 0, OP_BWD_INIT = 1, OP_BWD = 2, OP_FWD = 3 };
+enum OpKind : uint8_t { OP_EMIT = 0, OP_BWD_INIT = 1, OP_BWD = 2, OP_FWD = 3,
+                        OP_RUN = 4 /* engine-side fusion of consecutive tiny steps: c = index of the run */ };
 
 struct Op {
     OpKind kind;

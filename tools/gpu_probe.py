@@ -12,7 +12,8 @@ def run(name, p, budget=0, reps=3, kv=0):
     for _ in range(2): h.sweep()
     best = 1e9
     for _ in range(reps):
-        h.sweep(True); s = h.stats(); best = min(best, s['last_sweep_ms'])
+        h.sweep(False); best = min(best, h.stats()['last_sweep_ms'])
+    h.sweep(True)
     s = h.stats()
     S = st['state_columns']
     print(f"{name}: C={st['n_columns']} maxu={st['max_untagged']} states={S:.3e} arena={st['state_bytes_reserved']/2**30:.2f} GiB levels={st['checkpoint_levels']} "
