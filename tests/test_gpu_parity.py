@@ -79,6 +79,46 @@ def test_fp64_mode_is_tight(i):
     assert np.abs(capi.hmm_run(p, device=0, precision=1).values - oracle.oracle_run(p)).max() <= 1e-11
 
 
+def test_randomized_campaign_all_kernel_families():
+    # seeded random shapes (panel size, coverage, tags, alleles, gaps, missing panel entries) through every kernel
+    # family: 0 = auto, 1 = generic, 2 = pipelined/one CTA per SM, 3 = no 16-warp variant, 4 = no chain kernel
+    rng = np.random.default_rng(2024)
+    done = 0
+    while done < 48:
+        R = int(rng.choice([4, 6, 9, 10, 12, 16, 24, 33, 36, 64, 88, 128, 132, 200, 256, 400]))
+        max_cov = int(rng.integers(0, 8))
+        while (1 << max_cov) * R * R > (2e6 if R <= 128 else 4e6) and max_cov > 0:
+            max_cov -= 1
+        kw = dict(n_columns=int(rng.integers(2, 30 if R <= 128 else 10)), n_haps=R, coverage=float(rng.uniform(0.5, 12)),
+                  max_coverage=max(max_cov, 1), read_len_mean=float(rng.choice([400, 800, 1500, 3000])),
+                  tags="all" if max_cov == 0 else str(rng.choice(["none", "mixed", "all"])),
+                  multiallelic_frac=float(rng.choice([0.0, 0.1, 0.5, 1.0])), max_alleles=int(rng.choice([3, 4, 8, 16])),
+                  missing_frac=float(rng.choice([0.0, 0.005, 0.05])), gap_frac=float(rng.choice([0.0, 0.02, 0.3])),
+                  unknown_allele_frac=float(rng.choice([0.0, 0.1])), window=bool(rng.integers(2)),
+                  seed=int(rng.integers(1 << 30)))
+        p = make_problem(**kw)
+        want = oracle.oracle_run(p)
+        if np.isnan(want).any():
+            continue
+        for kv in (0, 1, 2, 3, 4):
+            assert_posteriors_close(capi.hmm_run(p, device=0, kernel_variant=kv).values, want)
+        done += 1
+
+
+def test_all_tagged_chain_matches_per_column_kernels():
+    # the regime of real runs (every read haplotagged, one block per column): chain kernel vs per-column launches
+    p = make_problem(400, 88, region_bp=60000, coverage=12, max_coverage=10, read_len_mean=3000, tags="all", seed=77,
+                     multiallelic_frac=0.2, max_alleles=6)
+    want = capi.hmm_run(p, device=0, precision=1).values
+    h = capi.Hmm(p, device=0)
+    h.sweep()
+    chain = h.fetch().values
+    assert h.stats()["n_launches"] < 20            # a handful of launches for 400 columns
+    h.close()
+    assert_posteriors_close(chain, want)
+    assert_posteriors_close(capi.hmm_run(p, device=0, kernel_variant=4).values, want)
+
+
 def test_single_column_and_empty_problem():
     p = make_problem(1, 6, coverage=0.0, seed=3)
     assert_posteriors_close(capi.hmm_run(p, device=0).values, oracle.oracle_run(p))
