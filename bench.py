@@ -96,9 +96,10 @@ class ClockSampler:
 # CPU baseline: the reference's own GenotypeHMM (oracle/_ref, compiled from the reference sources) or,
 # where that library is absent, the C restatement.  Bounded sample of the same workload shape.
 # ------------------------------------------------------------------------------------------------
-def cpu_sample_problems(n, sample_cols, sample_cov, n_haps):
+def cpu_sample_problems(n, sample_cols, sample_cov, n_haps, make=None):
     from giggles_b200.synth import config2_window
-    return [config2_window(sample_cols, seed=1000 + i, max_coverage=sample_cov, n_haps=n_haps) for i in range(n)]
+    make = make or config2_window
+    return [make(sample_cols, seed=1000 + i, max_coverage=sample_cov, n_haps=n_haps) for i in range(n)]
 
 
 def run_cpu_sample(problems, cores):
@@ -127,7 +128,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--columns", type=int, default=256, help="variant sites per window (one step sweeps one window)")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config1", "tagged", "config5"],
+                    help="config2 (default, the headline): chr20-scale window; the others are side measurements of the "
+                         "remaining BASELINE.json shapes")
+    ap.add_argument("--columns", type=int, default=None, help="variant sites per window (one step sweeps one window)")
     ap.add_argument("--max-coverage", type=int, default=15)
     ap.add_argument("--haps", type=int, default=88)
     ap.add_argument("--cpu-sample-cols", type=int, default=40)
@@ -136,18 +140,41 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    presets = {"config2": (256, 15, 88), "config1": (5000, 15, 10), "tagged": (20000, 15, 88), "config5": (48, 8, 400)}
+    d_cols, d_cov, d_haps = presets[args.workload]
+    if args.columns is None:
+        args.columns = d_cols
+    if args.workload != "config2":
+        args.max_coverage, args.haps = d_cov, d_haps
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
 
-    from giggles_b200.synth import config2_window
-    config = {"workload": f"configs[1] chr20-scale window: {args.columns} of 516k variant sites, {args.haps}-haplotype panel, "
-                          f"30x HiFi untagged, max-coverage {args.max_coverage} (<= 2^{args.max_coverage} x {args.haps}^2 states per column)",
+    from giggles_b200 import synth
+
+    def config2_window(n_columns, seed=2, max_coverage=15, n_haps=88):
+        if args.workload == "config1":
+            return synth.config1(seed=seed, n_columns=n_columns)
+        if args.workload == "tagged":
+            return synth.config2_window(n_columns, seed=seed, tags="all", n_haps=n_haps)
+        if args.workload == "config5":
+            return synth.config5_window(n_columns, seed=seed, n_haps=n_haps, max_coverage=max_coverage)
+        return synth.config2_window(n_columns, seed=seed, max_coverage=max_coverage, n_haps=n_haps)
+
+    names = {"config2": f"configs[1] chr20-scale window: {args.columns} of 516k variant sites, {args.haps}-haplotype panel, "
+                        f"30x HiFi untagged, max-coverage {args.max_coverage} (<= 2^{args.max_coverage} x {args.haps}^2 states per column)",
+             "config1": f"configs[0] 1 Mb region: {args.columns} variant sites, 10-haplotype panel, 10x HiFi untagged",
+             "tagged": f"configs[1] shape with every read haplotagged (the mode giggles runs in without --keep-untagged): "
+                       f"{args.columns} variant sites, {args.haps}-haplotype panel, one {args.haps}^2 block per column",
+             "config5": f"configs[4] shape: {args.columns} variant sites, {args.haps}-haplotype panel, 3..16 alleles per site, "
+                        f"max-coverage {args.max_coverage}"}
+    config = {"workload": names[args.workload],
               "columns_per_step": args.columns, "n_haps": args.haps, "max_coverage": args.max_coverage,
               "parallelism": f"{world} independent chain(s), one per GPU",
-              "l2_policy": "inputs larger than L2 (each column is up to 1 GB; L2 is 126 MB)"}
+              "l2_policy": ("inputs larger than L2 (each column is up to 1 GB; L2 is 126 MB)" if args.workload == "config2"
+                            else "side measurement: columns may fit L2; not the headline number")}
 
     # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
     if args.impl == "reference":
@@ -155,7 +182,7 @@ def main():
             return
         p_work = config2_window(args.columns, seed=2, max_coverage=args.max_coverage, n_haps=args.haps)
         states_per_col = p_work.state_columns() / p_work.n_columns
-        probs = cpu_sample_problems(cores, args.cpu_sample_cols, args.cpu_sample_cov, args.haps)
+        probs = cpu_sample_problems(cores, args.cpu_sample_cols, args.cpu_sample_cov, args.haps, config2_window)
         vals = []
         for i in range(args.warmup + args.steps):
             sc_s, _, dt, kind = run_cpu_sample(probs, cores)
@@ -197,7 +224,7 @@ def main():
         try:
             p_tmp = config2_window(args.columns, seed=2, max_coverage=args.max_coverage, n_haps=args.haps)
             spc = p_tmp.state_columns() / p_tmp.n_columns
-            probs = cpu_sample_problems(cores, args.cpu_sample_cols, args.cpu_sample_cov, args.haps)
+            probs = cpu_sample_problems(cores, args.cpu_sample_cols, args.cpu_sample_cov, args.haps, config2_window)
             sc_s, _, dt, kind = run_cpu_sample(probs, cores)
             cpu_baseline = {"value": sc_s / spc, "unit": UNIT, "cores": cores, "kind": kind,
                             "sample": f"{cores} chains x {args.cpu_sample_cols} columns, R={args.haps}, max-coverage "
@@ -284,7 +311,7 @@ def main():
     dominant = "forward" if fwd_ms >= bwd_ms else "backward"
     ach = fwd_gbs if dominant == "forward" else bwd_gbs
     roofline = {
-        "bound": "hbm", "kernel": f"step kernel, {dominant} (step_tma_kernel)", "achieved": ach, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": f"step kernel, {dominant} (" + ("chain_kernel" if args.workload == "tagged" else "step_tma_kernel") + ")", "achieved": ach, "peak": peak, "unit": "GB/s",
         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": (12.0 if dominant == "forward" else 8.0) * S / n_fwd,
         "avg_launch_ms": (fwd_ms / (n_fwd * args.steps)) if dominant == "forward" else (bwd_ms / (n_bwd * args.steps)),

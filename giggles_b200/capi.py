@@ -72,6 +72,8 @@ class gg_stats(C.Structure):
         ("last_fwd_ms", C.c_float),
         ("last_bwd_ms", C.c_float),
         ("last_emit_ms", C.c_float),
+        ("create_plan_ms", C.c_float),
+        ("create_total_ms", C.c_float),
         ("reserved", C.c_float),
     ]
 

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -704,7 +705,9 @@ int gg_hmm_create(const gg_problem *p, const gg_options *o, gg_hmm **out, char *
     int rc = guarded(err, errlen, [&] {
         if (!p || !out) throw std::runtime_error("gg_hmm_create: null argument");
         h = new gg_hmm();
+        const auto t_begin = std::chrono::steady_clock::now();
         build_plan(*p, h->plan);     // validates the problem before any device work
+        h->stats.create_plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         int ndev = 0;
         cudaError_t e = cudaGetDeviceCount(&ndev);
         if (e != cudaSuccess || ndev == 0) {
@@ -720,6 +723,7 @@ int gg_hmm_create(const gg_problem *p, const gg_options *o, gg_hmm **out, char *
         h->kernel_variant = o ? o->kernel_variant : 0;
         if (h->fp64) Engine<double>::create(h, o);
         else Engine<float>::create(h, o);
+        h->stats.create_total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     });
     if (rc != GG_OK) {
         delete h;

@@ -77,7 +77,6 @@ void build_plan(const gg_problem &p, Plan &pl) {
     std::vector<uint32_t> active, next_active, cursor(N, 0), prev_untagged, untagged;
     for (uint32_t k = 0; k < N; ++k) cursor[k] = p.read_entry_offset[k];
     uint32_t next_read = 0;
-    std::vector<uint16_t> order(R);
     for (uint32_t c = 0; c < C; ++c) {
         ColumnPlan &cp = pl.cols[c];
         const uint32_t nA = p.n_alleles[c];
@@ -92,11 +91,14 @@ void build_plan(const gg_problem &p, Plan &pl) {
             int32_t a = p.allele_ref[(size_t)c * R + h];
             require(a >= -1 && a < (int32_t)nA, "gg_problem: allele_ref out of range");
             pl.allele1[(size_t)c * R + h] = (uint8_t)(a + 1);
-            order[h] = (uint16_t)h;
         }
+        // stable counting sort of the haplotypes by allele class (<= 17 classes)
         const uint8_t *al = &pl.allele1[(size_t)c * R];
-        std::stable_sort(order.begin(), order.end(), [al](uint16_t x, uint16_t y) { return al[x] < al[y]; });
-        std::copy(order.begin(), order.end(), pl.row_order.begin() + (size_t)c * R);
+        uint32_t cnt[GG_MAX_ALLELES + 2] = {0};
+        for (uint32_t h = 0; h < R; ++h) ++cnt[al[h] + 1];
+        for (uint32_t k = 1; k <= GG_MAX_ALLELES + 1; ++k) cnt[k] += cnt[k - 1];
+        uint16_t *ro = &pl.row_order[(size_t)c * R];
+        for (uint32_t h = 0; h < R; ++h) ro[cnt[al[h]]++] = (uint16_t)h;
 
         // active set: keep spanning reads (in id order), append reads starting here
         next_active.clear();

@@ -100,6 +100,8 @@ typedef struct gg_stats {
     float last_fwd_ms;                /* ... of which forward step launches (timed sweeps only) */
     float last_bwd_ms;                /* ... backward step launches                             */
     float last_emit_ms;               /* emission-table launches                                */
+    float create_plan_ms;             /* host: column planner (gg_hmm_create)                    */
+    float create_total_ms;            /* host + device: planner, schedule, allocations, H2D      */
     float reserved;
 } gg_stats;
 
