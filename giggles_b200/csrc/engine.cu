@@ -23,6 +23,7 @@
 #include "hmm_kernels.cuh"
 #include "hmm_tma_kernel.cuh"
 #include "hmm_chain_kernel.cuh"
+#include "hmm_warp_kernel.cuh"
 #include "plan.hpp"
 #include "result.hpp"
 #include "schedule.hpp"
@@ -122,7 +123,7 @@ struct gg_hmm {
     Plan plan;
     Schedule sched;
     bool fp64 = false;
-    int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined, never two CTAs per SM, 3 = pipelined, never 16 consumer warps
+    int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined, never two CTAs per SM, 3 = pipelined, never 16 consumer warps, 4 = no chain kernel, 5 = no warp-per-block kernel
     bool tma_attr_done = false, chain_attr_done = false;
     int device = 0;
     int num_sms = 0;
@@ -279,6 +280,7 @@ struct Engine {
                 a.al_in = a.al_out;
             }
         }
+        if (try_launch_warp(h, a, pco, fwd)) return;
         if (try_launch_tma(h, a, pco, fwd)) return;
         const uint32_t rpi = 32 / h->shape.G;
         uint32_t nwarps = fwd ? h->shape.nwarps_fwd : h->shape.nwarps_bwd;
@@ -306,6 +308,44 @@ struct Engine {
         void *params[] = {(void *)&a};
         GG_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(threads), params, L.total, h->stream));
         ++h->stats.n_launches;
+    }
+
+    // Warp-per-block kernel for small panels (hmm_warp_kernel.cuh): fp32, R <= 32.
+    static const void *warp_kernel(bool fwd, int V, uint32_t ni) {
+#define GG_WK(VV, NN) if (V == VV && ni == NN) return fwd ? (const void *)step_warp_kernel<VV, NN, true> : (const void *)step_warp_kernel<VV, NN, false>;
+        GG_WK(1, 2) GG_WK(1, 4) GG_WK(1, 8) GG_WK(2, 2) GG_WK(2, 4) GG_WK(2, 8) GG_WK(2, 16) GG_WK(4, 2) GG_WK(4, 4) GG_WK(4, 8)
+#undef GG_WK
+        return nullptr;
+    }
+
+    static bool try_launch_warp(gg_hmm *h, const StepArgs<T> &a, const ColumnPlan &pco, bool fwd) {
+        if (sizeof(T) != 4 || h->kernel_variant == 1 || h->kernel_variant == 5 || a.in == nullptr || a.R > 32) return false;
+        const uint32_t rpi = 32 / a.G;
+        const uint32_t n_iter = (a.R + rpi - 1) / rpi;
+        const uint32_t ni = std::max<uint32_t>(2, pow2ceil(n_iter));
+        const void *k = warp_kernel(fwd, h->shape.V, ni);
+        if (!k) return false;
+        const size_t smem = fwd ? (size_t)kWarpKernelWarps * a.R * a.R * sizeof(float) : 16;
+        const int threads = 32 * kWarpKernelWarps;
+        auto key = std::make_tuple(k, threads, smem);
+        auto it = h->occ_cache.find(key);
+        int occ;
+        if (it == h->occ_cache.end()) {
+            GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem));
+            h->occ_cache[key] = occ;
+        } else {
+            occ = it->second;
+        }
+        if (occ < 1) return false;
+        const uint64_t n_items = (uint64_t)1 << pco.u;
+        uint32_t grid = (uint32_t)std::min<uint64_t>((n_items + kWarpKernelWarps - 1) / kWarpKernelWarps, (uint64_t)h->num_sms * occ);
+        grid = std::min(grid, h->max_grid);
+        StepArgs<float> af;
+        std::memcpy(&af, &a, sizeof(af));
+        void *params[] = {(void *)&af};
+        GG_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(threads), params, smem, h->stream));
+        ++h->stats.n_launches;
+        return true;
     }
 
     // Pipelined bulk-copy kernel (hmm_tma_kernel.cuh): fp32, R % 4 == 0, R <= 512.

@@ -100,7 +100,7 @@ def test_randomized_campaign_all_kernel_families():
         want = oracle.oracle_run(p)
         if np.isnan(want).any():
             continue
-        for kv in (0, 1, 2, 3, 4):
+        for kv in (0, 1, 2, 3, 4, 5):
             assert_posteriors_close(capi.hmm_run(p, device=0, kernel_variant=kv).values, want)
         done += 1
 

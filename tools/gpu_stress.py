@@ -32,7 +32,7 @@ while time.time() - t0 < budget_s:
     want = oracle.oracle_run(p)
     if np.isnan(want).any():
         continue
-    for kv in (0, 1, 2, 3, 4):
+    for kv in (0, 1, 2, 3, 4, 5):
         try:
             got = capi.hmm_run(p, device=0, kernel_variant=kv).values
         except Exception as e:
@@ -48,4 +48,4 @@ while time.time() - t0 < budget_s:
             bad += 1
             print("BAD", kv, kw, "rel", rel.max(), "abs", ab.max(), "nan", int(np.isnan(got).sum()), "maxu", int(p.untagged_per_column().max()), flush=True)
     n += 1
-print(f"stress: {n} problems x 5 kernel variants, {bad} failures, worst rel err on p>=1e-3: {worst:.2e}, {time.time()-t0:.0f} s")
+print(f"stress: {n} problems x 6 kernel variants, {bad} failures, worst rel err on p>=1e-3: {worst:.2e}, {time.time()-t0:.0f} s")
