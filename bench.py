@@ -310,9 +310,22 @@ def main():
     bwd_gbs = 8.0 * S * (n_bwd / max(n_fwd, 1)) * args.steps / (bwd_ms / 1e3) / 1e9
     dominant = "forward" if fwd_ms >= bwd_ms else "backward"
     ach = fwd_gbs if dominant == "forward" else bwd_gbs
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/, one launch of a
+    # u = 15 column of this workload: 2^15 x 88^2 states); null for the side workloads
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic_u15.json")
+    if args.workload == "config2" and os.path.exists(tpath):
+        try:
+            cap = json.load(open(tpath))[dominant][0]
+            traffic = (cap["dram_read"] + cap["dram_write"]) * 1e9
+            alg = (12.0 if dominant == "forward" else 8.0) * (1 << 15) * 88 * 88
+            traffic_note = (f"ncu dram__bytes_read+write of one {dominant} launch on a 2^15-block column: {traffic:.4g} B "
+                            f"against {alg:.4g} algorithmic bytes for that launch ({cap['duration_us']:.0f} us under ncu)")
+        except Exception:
+            pass
     roofline = {
         "bound": "hbm", "kernel": f"step kernel, {dominant} (" + ("chain_kernel" if args.workload == "tagged" else "step_tma_kernel") + ")", "achieved": ach, "peak": peak, "unit": "GB/s",
-        "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+        "frac": ach / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": (12.0 if dominant == "forward" else 8.0) * S / n_fwd,
         "avg_launch_ms": (fwd_ms / (n_fwd * args.steps)) if dominant == "forward" else (bwd_ms / (n_bwd * args.steps)),
         "forward": {"GBps": fwd_gbs, "frac": fwd_gbs / peak, "launches_per_step": n_fwd, "ms_per_step": fwd_ms / args.steps},

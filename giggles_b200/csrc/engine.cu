@@ -834,8 +834,33 @@ int gg_hmm_run(const gg_problem *p, const gg_options *o, gg_result **out, char *
     if (rc != GG_OK) return rc;
     rc = gg_hmm_sweep(h, 0, err, errlen);
     if (rc == GG_OK) rc = gg_hmm_fetch(h, out, err, errlen);
+    const bool was_fp32 = !h->fp64;
     gg_hmm_destroy(h);
-    return rc;
+    if (rc != GG_OK || !was_fp32) return rc;
+    // Range guard of the fp32 path: per-column scaling keeps well-conditioned chains far from underflow, but reads
+    // that contradict each other at 1e-10 per site over many sites can push every state of a column below fp32's
+    // range (the reference computes in 80-bit long double).  A non-finite posterior triggers ONE rerun on fp64 state;
+    // if that is non-finite too (e.g. a column whose panel alleles are all missing, where the reference itself
+    // returns NaN, SURVEY B-6) the fp64 result is returned as is.
+    bool finite = true;
+    for (double v : (*out)->values)
+        if (!std::isfinite(v)) { finite = false; break; }
+    if (finite) return GG_OK;
+    gg_options o64{};
+    if (o) o64 = *o;
+    o64.precision = 1;
+    gg_result *r64 = nullptr;
+    gg_hmm *h64 = nullptr;
+    char err2[256];
+    if (gg_hmm_create(p, &o64, &h64, err2, sizeof(err2)) != GG_OK) return GG_OK;      // keep the fp32 result
+    int rc2 = gg_hmm_sweep(h64, 0, err2, sizeof(err2));
+    if (rc2 == GG_OK) rc2 = gg_hmm_fetch(h64, &r64, err2, sizeof(err2));
+    gg_hmm_destroy(h64);
+    if (rc2 == GG_OK && r64) {
+        gg_result_free(*out);
+        *out = r64;
+    }
+    return GG_OK;
 }
 
 }  // extern "C"

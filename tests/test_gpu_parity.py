@@ -119,6 +119,27 @@ def test_all_tagged_chain_matches_per_column_kernels():
     assert_posteriors_close(capi.hmm_run(p, device=0, kernel_variant=4).values, want)
 
 
+def test_fp32_underflow_falls_back_to_fp64_state():
+    # five reads that all contradict the panel at 1e-10 each: every state of column 0 has emission 1e-50, below fp32
+    # range; the reference (80-bit) still gets the answer.  gg_hmm_run notices the non-finite fp32 result and reruns
+    # on fp64 state; the staged API (no guard) shows what the fp32 path alone produces.
+    from giggles_b200.problem import Problem
+    n = 5
+    p = Problem(positions=[100, 200], n_alleles=[2, 2], allele_ref=[[1, 1, 1, 1], [0, 1, 0, 1]], recomb=[0.01],
+                read_tag=[-1] * n, read_entry_offset=np.arange(0, 2 * n + 1, 2), entry_column=[0, 1] * n,
+                entry_allele=[0, 0] * n, entry_score_offset=np.arange(0, 4 * n + 1, 2),
+                entry_scores=[0.0, -30.0, 0.0, -1.0] * n)
+    want = oracle.oracle_run(p)
+    assert np.isfinite(want).all()
+    h = capi.Hmm(p, device=0)
+    h.sweep()
+    raw32 = h.fetch().values
+    h.close()
+    assert not np.isfinite(raw32).all()
+    got = capi.hmm_run(p, device=0).values
+    assert np.abs(got - want).max() <= 1e-11
+
+
 def test_single_column_and_empty_problem():
     p = make_problem(1, 6, coverage=0.0, seed=3)
     assert_posteriors_close(capi.hmm_run(p, device=0).values, oracle.oracle_run(p))
