@@ -83,7 +83,7 @@ class gg_stats(C.Structure):
 
 # every symbol include/giggles_b200.h declares (tests check that the library exports them all)
 SYMBOLS = [
-    "gg_hmm_run", "gg_hmm_create", "gg_hmm_sweep", "gg_hmm_fetch", "gg_hmm_stats", "gg_hmm_destroy", "gg_arena_release", "gg_hmm_debug_scales",
+    "gg_hmm_run", "gg_hmm_create", "gg_hmm_sweep", "gg_hmm_fetch", "gg_hmm_stats", "gg_hmm_destroy", "gg_arena_release", "gg_hmm_debug_scales", "gg_hmm_debug_op_times",
     "gg_result_likelihoods", "gg_result_n_columns", "gg_result_flat", "gg_result_free", "gg_result_call", "gg_result_from_host",
     "gg_plan_build", "gg_plan_n_columns", "gg_plan_active", "gg_plan_untagged", "gg_plan_shared_mask_prev",
     "gg_plan_compatible_prev", "gg_plan_free",
@@ -268,6 +268,14 @@ class Hmm:
         a, b = np.zeros(n), np.zeros(n)
         lib().gg_hmm_debug_scales(self._h, as_ptr(a, C.c_double), as_ptr(b, C.c_double))
         return a, b
+
+    def debug_op_times(self, cap=1 << 20):
+        k = np.zeros(cap, np.uint32); c = np.zeros(cap, np.uint32); ms = np.zeros(cap, np.float32)
+        f = lib().gg_hmm_debug_op_times
+        f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_float), C.c_uint64]
+        n = min(int(f(self._h, as_ptr(k, C.c_uint32), as_ptr(c, C.c_uint32), as_ptr(ms, C.c_float), cap)), cap)
+        return k[:n], c[:n], ms[:n]
 
     def stats(self) -> dict:
         s = gg_stats()

@@ -149,6 +149,7 @@ struct gg_hmm {
     std::map<std::tuple<const void *, int, size_t>, int> occ_cache;
     gg_stats stats{};
     std::vector<cudaEvent_t> ev;   // timing events (timed sweeps only)
+    std::vector<float> op_ms;      // per-op durations of the last timed sweep
     ~gg_hmm() {
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -349,11 +350,12 @@ struct Engine {
     }
 
     // Pipelined bulk-copy kernel (hmm_tma_kernel.cuh): fp32, R % 4 == 0, R <= 512.
-    static const void *tma_kernel(bool fwd, uint32_t G, int NS, bool mt, int cwt) {
-#define GG_TMA(GG, NN, MM, CC) if (G == GG && NS == NN && mt == MM && cwt == CC) return fwd ? (const void *)step_tma_kernel<true, GG, NN, MM, CC> : (const void *)step_tma_kernel<false, GG, NN, MM, CC>;
-        GG_TMA(1, 1, false, 8) GG_TMA(2, 1, false, 8) GG_TMA(4, 1, false, 8) GG_TMA(8, 1, false, 8) GG_TMA(16, 1, false, 8)
-        GG_TMA(32, 1, false, 8) GG_TMA(32, 1, false, 16)
-        GG_TMA(32, 1, true, 0) GG_TMA(32, 2, true, 0) GG_TMA(32, 4, true, 0)
+    static const void *tma_kernel(bool fwd, uint32_t G, int NS, bool mt, int cwt, bool two) {
+#define GG_TMA(GG, NN, MM, CC, TT) if (G == GG && NS == NN && mt == MM && cwt == CC && two == TT) return fwd ? (const void *)step_tma_kernel<true, GG, NN, MM, CC, TT> : (const void *)step_tma_kernel<false, GG, NN, MM, CC, TT>;
+        GG_TMA(1, 1, false, 8, false) GG_TMA(2, 1, false, 8, false) GG_TMA(4, 1, false, 8, false) GG_TMA(8, 1, false, 8, false)
+        GG_TMA(16, 1, false, 8, false) GG_TMA(32, 1, false, 8, false) GG_TMA(32, 1, false, 16, false)
+        GG_TMA(16, 1, false, 8, true) GG_TMA(32, 1, false, 8, true) GG_TMA(32, 1, false, 16, true)
+        GG_TMA(32, 1, true, 0, false) GG_TMA(32, 2, true, 0, false) GG_TMA(32, 4, true, 0, false)
 #undef GG_TMA
         return nullptr;
     }
@@ -364,14 +366,13 @@ struct Engine {
         const int NS = h->shape.NS;
         if (!h->tma_attr_done) {
             for (uint32_t g = 1; g <= 32; g <<= 1)
-                for (bool f : {false, true}) {
-                    GG_CUDA(cudaFuncSetAttribute(tma_kernel(f, g, 1, false, 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
-                    if (g == 32) {
-                        GG_CUDA(cudaFuncSetAttribute(tma_kernel(f, g, 1, false, 16), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
-                        for (int ns : {1, 2, 4})
-                            GG_CUDA(cudaFuncSetAttribute(tma_kernel(f, g, ns, true, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
-                    }
-                }
+                for (bool f : {false, true})
+                    for (int ns : {1, 2, 4})
+                        for (bool mt : {false, true})
+                            for (int cwt : {0, 8, 16})
+                                for (bool tw : {false, true})
+                                    if (const void *kk = tma_kernel(f, g, ns, mt, cwt, tw))
+                                        GG_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
             h->tma_attr_done = true;
         }
         const uint32_t rpi = 32 / a.G;
@@ -380,10 +381,11 @@ struct Engine {
         // geometry search.  Whole block = one tile (R <= 128): two CTAs of 8 consumer warps per SM when the column's
         // footprint fits twice, else one CTA of 16 (same warp count, deeper ring), else one of 8.  Larger R: row tiles
         // of <= ~40 KB, most consumer warps first, >= 3 stages.
+        const bool two_ok = nred == 2 && a.G >= 16 && NS == 1 && a.R <= 128;   // both blocks of the reduce set held in stages
         struct Pick { uint32_t cw, tr, stages, ctas; int cwt; TmaGeom L; bool ok; } pick{};
         auto fit = [&](uint32_t cw, uint32_t tr, uint32_t lo, uint32_t hi, size_t cap, uint32_t &stages, TmaGeom &L) {
             for (stages = hi; stages >= lo; --stages) {
-                L = tma_geom(a.R, tr, stages, cw * rpi, ncls, fwd, nred > 1);
+                L = tma_geom(a.R, tr, stages, cw * rpi, ncls, fwd, nred > 1 && !(two_ok && tr == a.R));
                 if (L.total <= cap) return true;
             }
             return false;
@@ -409,7 +411,7 @@ struct Engine {
             }
         }
         if (!pick.ok) return false;
-        const void *k = tma_kernel(fwd, a.G, NS, pick.cwt == 0, pick.cwt);
+        const void *k = tma_kernel(fwd, a.G, NS, pick.cwt == 0, pick.cwt, two_ok && pick.cwt != 0);
         if (!k) return false;
         const int threads = 32 * (1 + (int)pick.cw);
         auto key = std::make_tuple(k, threads, (size_t)pick.L.total);
@@ -605,7 +607,7 @@ struct Engine {
         if (budget == 0) {
             size_t free_b = 0, total_b = 0;
             GG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            budget = (uint64_t)((free_b + g_arena_cache.cached(h->device)) * 0.8);   // the retired arena is ours to reuse
+            budget = (uint64_t)((free_b + g_arena_cache.cached(h->device)) * 0.9);   // the retired arena is ours to reuse
         }
         // if everything fits there is no reason to reserve more than that
         uint64_t all = 0;
@@ -691,9 +693,11 @@ struct Engine {
         st.last_fwdbwd_kernel_ms = 0.f;
         st.last_fwd_ms = st.last_bwd_ms = st.last_emit_ms = 0.f;
         if (per_kernel) {
+            h->op_ms.assign(nops, 0.f);
             for (size_t i = 0; i < nops; ++i) {
                 float ms = 0.f;
                 GG_CUDA(cudaEventElapsedTime(&ms, h->ev[2 + 2 * i], h->ev[3 + 2 * i]));
+                h->op_ms[i] = ms;
                 switch (ops[i].kind) {
                 case OP_EMIT: st.last_emit_ms += ms; break;
                 case OP_FWD: st.last_fwd_ms += ms; break;
@@ -817,6 +821,20 @@ void gg_hmm_destroy(gg_hmm *h) {
 }
 
 void gg_arena_release(void) { g_arena_cache.clear(); }
+
+// per-op record of the last timed sweep: kind (OpKind), produced column (EMIT: first column; RUN: first produced column),
+// duration in ms.  Returns the number of ops (may exceed cap).
+uint64_t gg_hmm_debug_op_times(gg_hmm *h, uint32_t *kind, uint32_t *column, float *ms, uint64_t cap) {
+    if (!h) return 0;
+    const size_t n = std::min(h->exec_ops.size(), h->op_ms.size());
+    for (size_t i = 0; i < n && i < cap; ++i) {
+        const Op &op = h->exec_ops[i];
+        kind[i] = (uint32_t)op.kind + (op.kind == OP_RUN && h->runs[op.c].fwd ? 100u : 0u);
+        column[i] = op.kind == OP_RUN ? h->chain_steps[h->runs[op.c].first].c_out : op.c;
+        ms[i] = h->op_ms[i];
+    }
+    return n;
+}
 
 int gg_hmm_debug_scales(gg_hmm *h, double *alpha_scale, double *beta_scale) {
     if (!h) return GG_ERR_INVALID;

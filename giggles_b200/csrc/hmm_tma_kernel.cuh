@@ -98,7 +98,9 @@ __device__ __forceinline__ uint2 pack_row(uint32_t R1, uint32_t row0, uint32_t R
 // MT = false: a block is one tile (TR == R), known at compile time so the tile loop and its bookkeeping vanish.
 // CWT: consumer warps at compile time (8: two CTAs per SM; 16: one CTA per SM when the shared-memory footprint of a
 // column - reduce-set accumulator, many allele classes - does not fit twice); 0 = taken from blockDim.
-template <bool FWD, int G, int NS, bool MT, int CWT>
+// TWO: the reduce set has exactly two blocks and both are held in stages (compile-time so that the common
+// one-block kernels carry none of its code).
+template <bool FWD, int G, int NS, bool MT, int CWT, bool TWO>
 __global__ void __launch_bounds__(32 * (1 + (CWT ? CWT : kTmaMaxConsumerWarps)), (CWT == 8 ? 2 : 1))
 step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t TR_arg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -123,7 +125,11 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
     const uint32_t nred = FWD ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
     const uint32_t n_bcast = FWD ? (a.u_out - a.n_sh) : a.n_free_left;
     const uint32_t nload = nred + (FWD ? 1u : 0u);      // loads per tile
-    const TmaGeom L = tma_geom(R, TR, n_stages, ngrp, NCo, FWD, nred > 1);
+    // reduce sets of two (one read starts / ends between the columns: the common non-trivial case) are summed on
+    // the fly from two stages; longer ones (and all of them when a block is tiled) are folded into an accumulator
+    constexpr bool two = TWO;
+    const bool accum = !TWO && nred > 1;
+    const TmaGeom L = tma_geom(R, TR, n_stages, ngrp, NCo, FWD, accum);
     const uint32_t n_tiles = MT ? L.n_tiles : 1u;
     TmaStageMeta *s_meta = reinterpret_cast<TmaStageMeta *>(smem_raw + L.off_meta);
     const uint32_t n_items = 1u << a.u_out;
@@ -298,7 +304,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
     };
 
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, parity_item ^= 1u) {
-        float kx[NS][4], kr[NS][4], kc[NS][4], gout[NS][4], colacc[NS][4];
+        float kx[NS][4], kx1[NS][4], kr[NS][4], kc[NS][4], gout[NS][4], colacc[NS][4];
         float totacc = 0.f, totv = 0.f;
         const float *fgo = nullptr, *fgi = nullptr;
         float *outp = nullptr;
@@ -314,7 +320,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
             const float *xs = reinterpret_cast<const float *>(smem_raw + L.off_stage + s0 * L.stage_bytes);
             const float *side = reinterpret_cast<const float *>(smem_raw + L.off_stage + s0 * L.stage_bytes + L.side_off);
             bool early_release = false;
-            if (nred > 1) {
+            if (accum) {
                 // fold the reduce set into s_acc (and, on the first tile, the side records into s_side); every thread
                 // owns the same elements for all k.  Nothing is held across the loop: the set may exceed the ring.
                 for (uint32_t k = 0; k < nred; ++k) {
@@ -323,6 +329,11 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                     const unsigned char *stb = smem_raw + L.off_stage + sk * L.stage_bytes;
                     const float *st = reinterpret_cast<const float *>(stb);
                     const float *fgk = s_meta[sk].fg_self;
+                    float gk[NS][4];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) gk[s][v] = FWD ? 1.f : fgk[NCi + a2i[s][v]];
                     for (uint32_t it = 0; it < L.n_iter_t; ++it) {
                         const uint32_t rl = it * ngrp + grp;     // row inside the tile, natural order
                         if (rl < rows) {
@@ -332,10 +343,10 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                                 if (cok[s]) {
                                     float4 v = *reinterpret_cast<const float4 *>(st + rl * R + ccol[s]);
                                     if (!FWD) {
-                                        v.x *= fk * fgk[NCi + a2i[s][0]];
-                                        v.y *= fk * fgk[NCi + a2i[s][1]];
-                                        v.z *= fk * fgk[NCi + a2i[s][2]];
-                                        v.w *= fk * fgk[NCi + a2i[s][3]];
+                                        v.x *= fk * gk[s][0];
+                                        v.y *= fk * gk[s][1];
+                                        v.z *= fk * gk[s][2];
+                                        v.w *= fk * gk[s][3];
                                     }
                                     float4 *dst = reinterpret_cast<float4 *>(s_acc + rl * R + ccol[s]);
                                     if (k > 0) {
@@ -364,7 +375,17 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                 for (uint32_t q = ctid; q < fgs_o; q += nct) s_fgo[q] = m0->fg_out[q];
                 consumer_bar(nct);
             }
-            if (nred > 1 || multi) side = s_side;
+            if (accum || multi) side = s_side;
+            const float *xs1 = xs, *side1 = side;
+            const TmaStageMeta *m1 = m0;
+            uint32_t s1 = 0;
+            if (two) {
+                s1 = (seq + 1) % n_stages;
+                mbar_wait(&s_full[s1], ((seq + 1) / n_stages) & 1u);
+                m1 = &s_meta[s1];
+                xs1 = reinterpret_cast<const float *>(smem_raw + L.off_stage + s1 * L.stage_bytes);
+                side1 = reinterpret_cast<const float *>(smem_raw + L.off_stage + s1 * L.stage_bytes + L.side_off);
+            }
             const float *bs = xs;
             uint32_t sb = 0;
             if (FWD) {
@@ -379,17 +400,18 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                 // The reference zeroes beta where an allele of the pair is missing at c-1 (src/genotypehmm.cpp:309);
                 // those states have emission 0 (F/G slot 0), so they reach neither the next backward step nor any
                 // posterior and the mask is not applied here (the value stays finite).
-                fgo = (nred > 1 || multi) ? s_fgo : m0->fg_out;
-                weigh = !FWD && nred == 1;
-                totv = side[2 * R];
+                fgo = (accum || multi) ? s_fgo : m0->fg_out;
+                weigh = !FWD && !accum;
+                totv = side[2 * R] + (two ? side1[2 * R] : 0.f);
                 const float ctot = cC * totv;
                 outp = a.out + (uint64_t)b_out * BS;
 #pragma unroll
                 for (int s = 0; s < NS; ++s)
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
-                        const float cb = cB * side[R + ccol[s] + v] + ctot;
+                        const float cb = cB * (side[R + ccol[s] + v] + (two ? side1[R + ccol[s] + v] : 0.f)) + ctot;
                         gout[s][v] = fgo[NCo + a2o[s][v]];
+                        kx1[s][v] = (two && !FWD) ? cA * m1->fg_self[NCi + a2i[s][v]] : 0.f;
                         if (FWD) {
                             kx[s][v] = gout[s][v] * cA; kr[s][v] = gout[s][v]; kc[s][v] = gout[s][v] * cb;
                         } else {
@@ -402,11 +424,14 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
             const char *xrow = reinterpret_cast<const char *>(side);
             const char *fgo_b = reinterpret_cast<const char *>(fgo);
             const char *fgi_b = reinterpret_cast<const char *>(fgi);
-            const char *xcolp[NS], *bcolp[NS];
+            const char *xcolp[NS], *xcolp1[NS], *bcolp[NS];
             char *ocolp[NS];
+            const char *xrow1 = reinterpret_cast<const char *>(side1);
+            const char *fgi1_b = reinterpret_cast<const char *>(m1->fg_self);
 #pragma unroll
             for (int s = 0; s < NS; ++s) {      // per-lane column pointers: the row loop only adds the row offset
                 xcolp[s] = reinterpret_cast<const char *>(xs + ccol[s]);
+                xcolp1[s] = reinterpret_cast<const char *>(xs1 + ccol[s]);
                 bcolp[s] = reinterpret_cast<const char *>(bs + ccol[s]);
                 ocolp[s] = reinterpret_cast<char *>(outp + (uint64_t)row0 * R + ccol[s]);
             }
@@ -418,7 +443,13 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                 const uint32_t rowb = meta.x & 0x7fffffffu;
                 const uint32_t r1b = meta.y & 0xfffu, a1ob = (meta.y >> 12) & 0x7fu, a1ib = (meta.y >> 19) & 0x7fu;
                 const bool rvalid = (int32_t)meta.x < 0;
-                const float rowterm = cB * *reinterpret_cast<const float *>(xrow + r1b);
+                float rowsum_in = *reinterpret_cast<const float *>(xrow + r1b);
+                float fk1 = 0.f;
+                if (two) {
+                    rowsum_in += *reinterpret_cast<const float *>(xrow1 + r1b);
+                    if (!FWD) fk1 = *reinterpret_cast<const float *>(fgi1_b + a1ib);
+                }
+                const float rowterm = cB * rowsum_in;
                 const float fo = *reinterpret_cast<const float *>(fgo_b + a1ob);
                 const float fk = weigh ? *reinterpret_cast<const float *>(fgi_b + a1ib) : 1.f;
                 if (FWD && a1ob != cur_cls) {         // row class changed: park the posterior accumulators
@@ -429,7 +460,13 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
                     const float4 xv = *reinterpret_cast<const float4 *>(xcolp[s] + rowb);
-                    const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+                    float x[4] = {xv.x, xv.y, xv.z, xv.w};
+                    float x1[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (two) {
+                        const float4 yv = *reinterpret_cast<const float4 *>(xcolp1[s] + rowb);
+                        if (FWD) { x[0] += yv.x; x[1] += yv.y; x[2] += yv.z; x[3] += yv.w; }
+                        else { x1[0] = fk1 * yv.x; x1[1] = fk1 * yv.y; x1[2] = fk1 * yv.z; x1[3] = fk1 * yv.w; }
+                    }
                     float o[4];
                     if (FWD) {
 #pragma unroll
@@ -442,7 +479,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                         float dot = 0.f;
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
-                            o[v] = fmaf(kx[s][v], fk * x[v], rowterm + kc[s][v]);
+                            o[v] = fmaf(kx[s][v], fk * x[v], fmaf(kx1[s][v], x1[v], rowterm + kc[s][v]));
                             dot = fmaf(o[v], gout[s][v], dot);
                             colacc[s][v] = fmaf(fo, o[v], colacc[s][v]);      // times gout once per block, below
                         }
@@ -464,10 +501,11 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
             __syncwarp();
             if (lane == 0) {
                 if (!early_release) mbar_arrive(&s_empty[s0]);
+                if (two) mbar_arrive(&s_empty[s1]);
                 if (FWD) mbar_arrive(&s_empty[sb]);
             }
             seq += nload;
-            if (nred > 1 && t + 1 < n_tiles) consumer_bar(nct);   // s_acc is rewritten by the next tile
+            if (accum && t + 1 < n_tiles) consumer_bar(nct);   // s_acc is rewritten by the next tile
         }
         // backward: the column scale.  Without missing alleles sum(beta_{c-1}[b']) equals the reduced input total
         // exactly (tA + 2R tB + R^2 tC = 1); any positive scalar of that magnitude serves, so use it.

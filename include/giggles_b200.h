@@ -75,7 +75,7 @@ typedef struct gg_problem {
 
 typedef struct gg_options {
     int32_t device;                   /* CUDA ordinal; -1 = current device      */
-    uint64_t state_budget_bytes;      /* HBM budget for alpha/beta columns; 0 = 80 % of free memory */
+    uint64_t state_budget_bytes;      /* HBM budget for alpha/beta columns; 0 = 90 % of free memory */
     int32_t precision;                /* 0 = fp32 state with per-column scaling (production); 1 = fp64 state (validation) */
     int32_t kernel_variant;           /* 0 = auto; 1 = generic step kernel only (no bulk-copy pipeline), for A/B tests */
 } gg_options;
@@ -124,6 +124,9 @@ void gg_hmm_destroy(gg_hmm *h);
 void gg_arena_release(void);
 /* test hook: the per-column sums of the stored (unnormalised) alpha / beta columns of the last sweep, [n_columns] each */
 int gg_hmm_debug_scales(gg_hmm *h, double *alpha_scale, double *beta_scale);
+/* test/profiling hook: per-launch record of the last TIMED sweep (kind: 0 emission, 1 backward init, 2 backward step,
+ * 3 forward step, 4 fused backward run, 104 fused forward run; the column it produced; CUDA-event milliseconds) */
+uint64_t gg_hmm_debug_op_times(gg_hmm *h, uint32_t *kind, uint32_t *column, float *ms, uint64_t cap);
 
 /* ---- result access: replaces GenotypeHMM::get_genotype_likelihoods
  *      (src/genotypehmm.cpp:563-574, giggles/core.pyx:505-506).  Returns a pointer
