@@ -83,7 +83,7 @@ class gg_stats(C.Structure):
 
 # every symbol include/giggles_b200.h declares (tests check that the library exports them all)
 SYMBOLS = [
-    "gg_hmm_run", "gg_hmm_create", "gg_hmm_sweep", "gg_hmm_fetch", "gg_hmm_stats", "gg_hmm_destroy", "gg_arena_release", "gg_hmm_debug_scales", "gg_hmm_debug_op_times",
+    "gg_hmm_run", "gg_hmm_run_batch", "gg_hmm_create", "gg_hmm_sweep", "gg_hmm_fetch", "gg_hmm_stats", "gg_hmm_destroy", "gg_arena_release", "gg_hmm_debug_scales", "gg_hmm_debug_op_times",
     "gg_result_likelihoods", "gg_result_n_columns", "gg_result_flat", "gg_result_free", "gg_result_call", "gg_result_from_host",
     "gg_plan_build", "gg_plan_n_columns", "gg_plan_active", "gg_plan_untagged", "gg_plan_shared_mask_prev",
     "gg_plan_compatible_prev", "gg_plan_free",
@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
     vp, u32, u64, i32, dbl = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32, C.c_double
     errargs = [C.c_char_p, C.c_size_t]
     L.gg_hmm_run.argtypes = [C.POINTER(gg_problem), C.POINTER(gg_options), C.POINTER(vp)] + errargs
+    L.gg_hmm_run_batch.argtypes = [C.POINTER(gg_problem), u32, C.POINTER(gg_options), C.POINTER(vp)] + errargs
     L.gg_hmm_create.argtypes = [C.POINTER(gg_problem), C.POINTER(gg_options), C.POINTER(vp)] + errargs
     L.gg_hmm_sweep.argtypes = [vp, C.c_int] + errargs
     L.gg_hmm_fetch.argtypes = [vp, C.POINTER(vp)] + errargs
@@ -240,6 +241,19 @@ def hmm_run(p: Problem | CProblem, device: int = -1, budget: int = 0, precision:
     o = _options(device, budget, precision, kernel_variant)
     _check(lib().gg_hmm_run(C.byref(cp.struct), C.byref(o), C.byref(out), err, len(err)), err)
     return Result(out)
+
+
+def hmm_run_batch(problems, device: int = -1, budget: int = 0, precision: int = 0, kernel_variant: int = 0):
+    """``gg_hmm_run_batch``: independent chains back to back, host planning of chain i+1 overlapped with the sweep of i."""
+    cps = [p if isinstance(p, CProblem) else CProblem(p) for p in problems]
+    arr = (gg_problem * len(cps))(*[cp.struct for cp in cps])
+    outs = (C.c_void_p * len(cps))()
+    err = C.create_string_buffer(512)
+    o = _options(device, budget, precision, kernel_variant)
+    rc = lib().gg_hmm_run_batch(arr, len(cps), C.byref(o), outs, err, len(err))
+    res = [Result(C.c_void_p(outs[i])) if outs[i] else None for i in range(len(cps))]
+    _check(rc, err)
+    return res
 
 
 class Hmm:

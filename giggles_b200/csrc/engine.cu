@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -130,6 +132,7 @@ struct gg_hmm {
     size_t elem = 4;
     cudaStream_t stream = nullptr;
     std::vector<uint64_t> colb, fgb, fg_prefix_elems;
+    std::vector<ColDesc> host_cols;
     DevBuf<ColDesc> d_cols;
     DevBuf<uint8_t> d_em_side, d_allele1;
     DevBuf<double> d_em_prob, d_scale_a, d_scale_b, d_result;
@@ -524,7 +527,6 @@ struct Engine {
             h->exec_ops.push_back(fused);
             i = j;
         }
-        if (!h->chain_steps.empty()) h->d_chain_steps.upload(h->chain_steps, h->stream);
     }
 
     static void launch_run(gg_hmm *h, const Op &op) {
@@ -568,52 +570,36 @@ struct Engine {
         done = true;
     }
 
-    static void create(gg_hmm *h, const gg_options *o) {
+    // ---- host half of gg_hmm_create: sizes, checkpoint schedule, run fusion.  No CUDA call: a worker thread can do it
+    //      for chain i+1 while the device sweeps chain i (gg_hmm_run_batch).
+    static void prepare_host(gg_hmm *h, uint64_t budget) {
         Plan &pl = h->plan;
         const uint32_t C = pl.n_columns, R = pl.n_haps;
         h->elem = sizeof(T);
         h->shape = choose_shape<T>(R);
-        set_attrs();
         h->colb.resize(C);
         h->fgb.resize(C);
         h->fg_prefix_elems.assign(C + 1, 0);
-        std::vector<ColDesc> cd(C);
+        h->host_cols.assign(C, ColDesc{});
         for (uint32_t c = 0; c < C; ++c) {
             const ColumnPlan &cp = pl.cols[c];
             h->colb[c] = col_elems(cp.u, R) * sizeof(T);
             h->fgb[c] = fg_elems(cp.u, cp.n_alleles) * sizeof(T);
             h->fg_prefix_elems[c + 1] = h->fg_prefix_elems[c] + fg_elems(cp.u, cp.n_alleles);
-            cd[c].u = cp.u;
-            cd[c].n_alleles = cp.n_alleles;
-            cd[c].em_count = cp.em_count;
-            cd[c].em_off = cp.em_off;
-            cd[c].em_prob_off = cp.em_prob_off;
-            cd[c].fg_prefix = h->fg_prefix_elems[c];
-        }
-        // static tables first, then size the arena from what is left
-        h->d_cols.upload(cd, h->stream);
-        h->d_em_side.upload(pl.em_side, h->stream);
-        h->d_em_prob.upload(pl.em_prob, h->stream);
-        h->d_allele1.upload(pl.allele1, h->stream);
-        h->d_row_order.upload(pl.row_order, h->stream);
-        h->d_scale_a.alloc(C);
-        h->d_scale_b.alloc(C);
-        h->d_result.alloc(pl.gl_offsets[C]);
-        h->d_counter.alloc(1);
-        GG_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned int), h->stream));
-        h->max_grid = (uint32_t)h->num_sms * 16;
-        h->d_partial.alloc((size_t)h->max_grid * kPartialStride * sizeof(T));
-        uint64_t budget = o ? o->state_budget_bytes : 0;
-        if (budget == 0) {
-            size_t free_b = 0, total_b = 0;
-            GG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            budget = (uint64_t)((free_b + g_arena_cache.cached(h->device)) * 0.9);   // the retired arena is ours to reuse
+            ColDesc &cd = h->host_cols[c];
+            cd.u = cp.u;
+            cd.n_alleles = cp.n_alleles;
+            cd.em_count = cp.em_count;
+            cd.em_off = cp.em_off;
+            cd.em_prob_off = cp.em_prob_off;
+            cd.fg_prefix = h->fg_prefix_elems[c];
         }
         // if everything fits there is no reason to reserve more than that
-        uint64_t all = 0;
-        for (uint32_t c = 0; c < C; ++c) all += h->colb[c] + h->fgb[c] + 512;
-        uint64_t maxcol = 0;
-        for (uint32_t c = 0; c < C; ++c) maxcol = std::max(maxcol, h->colb[c]);
+        uint64_t all = 0, maxcol = 0;
+        for (uint32_t c = 0; c < C; ++c) {
+            all += h->colb[c] + h->fgb[c] + 512;
+            maxcol = std::max(maxcol, h->colb[c]);
+        }
         budget = std::min<uint64_t>(budget, all + 3 * maxcol + 4096);
         try {
             build_schedule(h->colb, h->fgb, budget, h->sched);
@@ -625,6 +611,26 @@ struct Engine {
             throw CudaError(m.find("budget") != std::string::npos ? GG_ERR_NOMEM : GG_ERR_INVALID, m);
         }
         fuse_runs(h);
+    }
+
+    // ---- device half: static tables H2D, arena
+    static void create_device(gg_hmm *h) {
+        Plan &pl = h->plan;
+        const uint32_t C = pl.n_columns;
+        set_attrs();
+        h->d_cols.upload(h->host_cols, h->stream);
+        h->d_em_side.upload(pl.em_side, h->stream);
+        h->d_em_prob.upload(pl.em_prob, h->stream);
+        h->d_allele1.upload(pl.allele1, h->stream);
+        h->d_row_order.upload(pl.row_order, h->stream);
+        if (!h->chain_steps.empty()) h->d_chain_steps.upload(h->chain_steps, h->stream);
+        h->d_scale_a.alloc(C);
+        h->d_scale_b.alloc(C);
+        h->d_result.alloc(pl.gl_offsets[C]);
+        h->d_counter.alloc(1);
+        GG_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned int), h->stream));
+        h->max_grid = (uint32_t)h->num_sms * 16;
+        h->d_partial.alloc((size_t)h->max_grid * kPartialStride * sizeof(T));
         h->arena = g_arena_cache.take(h->device, h->sched.arena_bytes, h->arena_bytes);
         if (!h->arena && h->sched.arena_bytes) {
             GG_CUDA(cudaMalloc(&h->arena, h->sched.arena_bytes));
@@ -639,6 +645,7 @@ struct Engine {
         if (pl.gl_offsets[C]) GG_CUDA(cudaMemsetAsync(h->d_result.p, 0, pl.gl_offsets[C] * sizeof(double), h->stream));
         GG_CUDA(cudaStreamSynchronize(h->stream));
         // stats that do not depend on a sweep
+        const uint32_t R = pl.n_haps;
         gg_stats &st = h->stats;
         st.n_columns = C;
         st.state_columns = pl.state_columns;
@@ -743,31 +750,74 @@ int gg_device_count(void) {
     return n;
 }
 
+// budget for the state arena: the caller's, or 90 % of what is free (the retired arena of the last handle counts as free)
+static uint64_t default_budget(const gg_options *o, int device) {
+    uint64_t budget = o ? o->state_budget_bytes : 0;
+    if (budget == 0) {
+        size_t free_b = 0, total_b = 0;
+        GG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        budget = (uint64_t)((free_b + g_arena_cache.cached(device)) * 0.9);
+    }
+    return budget;
+}
+
+static void need_device(const gg_options *o, int *device, int *num_sms) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        throw CudaError(GG_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+    }
+    const int dev = o ? o->device : -1;
+    if (dev >= 0) GG_CUDA(cudaSetDevice(dev));
+    GG_CUDA(cudaGetDevice(device));
+    GG_CUDA(cudaDeviceGetAttribute(num_sms, cudaDevAttrMultiProcessorCount, *device));
+}
+
+// host-only halves of create (no CUDA calls): validate + plan, then schedule + run fusion
+static gg_hmm *hmm_plan(const gg_problem *p, const gg_options *o) {
+    gg_hmm *h = new gg_hmm();
+    try {
+        const auto t_begin = std::chrono::steady_clock::now();
+        build_plan(*p, h->plan);
+        h->stats.create_plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        h->stats.create_total_ms = h->stats.create_plan_ms;
+        h->fp64 = o && o->precision == 1;
+        h->kernel_variant = o ? o->kernel_variant : 0;
+    } catch (...) {
+        delete h;
+        throw;
+    }
+    return h;
+}
+
+static void hmm_schedule(gg_hmm *h, uint64_t budget) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    if (h->fp64) Engine<double>::prepare_host(h, budget);
+    else Engine<float>::prepare_host(h, budget);
+    h->stats.create_total_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+}
+
+static void hmm_create_device(gg_hmm *h, int device, int num_sms) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    h->device = device;
+    h->num_sms = num_sms;
+    GG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (h->fp64) Engine<double>::create_device(h);
+    else Engine<float>::create_device(h);
+    h->stats.create_total_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+}
+
 int gg_hmm_create(const gg_problem *p, const gg_options *o, gg_hmm **out, char *err, size_t errlen) {
     if (out) *out = nullptr;
     gg_hmm *h = nullptr;
     int rc = guarded(err, errlen, [&] {
         if (!p || !out) throw std::runtime_error("gg_hmm_create: null argument");
-        h = new gg_hmm();
-        const auto t_begin = std::chrono::steady_clock::now();
-        build_plan(*p, h->plan);     // validates the problem before any device work
-        h->stats.create_plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-        int ndev = 0;
-        cudaError_t e = cudaGetDeviceCount(&ndev);
-        if (e != cudaSuccess || ndev == 0) {
-            cudaGetLastError();
-            throw CudaError(GG_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
-        }
-        int dev = o ? o->device : -1;
-        if (dev >= 0) GG_CUDA(cudaSetDevice(dev));
-        GG_CUDA(cudaGetDevice(&h->device));
-        GG_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
-        GG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-        h->fp64 = o && o->precision == 1;
-        h->kernel_variant = o ? o->kernel_variant : 0;
-        if (h->fp64) Engine<double>::create(h, o);
-        else Engine<float>::create(h, o);
-        h->stats.create_total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        h = hmm_plan(p, o);          // validates the problem before any device work
+        int device = 0, num_sms = 0;
+        need_device(o, &device, &num_sms);
+        hmm_schedule(h, default_budget(o, device));
+        hmm_create_device(h, device, num_sms);
     });
     if (rc != GG_OK) {
         delete h;
@@ -821,6 +871,64 @@ void gg_hmm_destroy(gg_hmm *h) {
 }
 
 void gg_arena_release(void) { g_arena_cache.clear(); }
+
+// Independent chains back to back on one device; chain i+1 is planned and scheduled on a host thread while the device
+// sweeps chain i (the reference plans and sweeps one chromosome after the other, giggles/cli/genotype.py:196-338).
+int gg_hmm_run_batch(const gg_problem *problems, uint32_t n, const gg_options *o, gg_result **results, char *err, size_t errlen) {
+    if (results)
+        for (uint32_t i = 0; i < n; ++i) results[i] = nullptr;
+    return guarded(err, errlen, [&] {
+        if ((!problems || !results) && n) throw std::runtime_error("gg_hmm_run_batch: null argument");
+        if (n == 0) return;
+        gg_hmm *first = hmm_plan(&problems[0], o);
+        std::unique_ptr<gg_hmm> cur(first);
+        int device = 0, num_sms = 0;
+        need_device(o, &device, &num_sms);
+        const uint64_t budget = default_budget(o, device);
+        hmm_schedule(cur.get(), budget);
+        for (uint32_t i = 0; i < n; ++i) {
+            std::future<gg_hmm *> next;
+            if (i + 1 < n)
+                next = std::async(std::launch::async, [&, i] {
+                    gg_hmm *h = hmm_plan(&problems[i + 1], o);
+                    try { hmm_schedule(h, budget); } catch (...) { delete h; throw; }
+                    return h;
+                });
+            char e2[512] = {0};
+            int rc = GG_OK;
+            const bool trace = std::getenv("GG_TRACE") != nullptr;
+            const auto t0 = std::chrono::steady_clock::now();
+            auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t).count(); };
+            try {
+                hmm_create_device(cur.get(), device, num_sms);
+            } catch (...) {
+                if (next.valid()) { try { delete next.get(); } catch (...) {} }
+                throw;
+            }
+            const float t_dev = ms_since(t0);
+            rc = gg_hmm_sweep(cur.get(), 0, e2, sizeof(e2));
+            const float t_sweep = ms_since(t0);
+            if (rc == GG_OK) rc = gg_hmm_fetch(cur.get(), &results[i], e2, sizeof(e2));
+            const float t_fetch = ms_since(t0);
+            cudaSetDevice(device);
+            const float host_ms = cur->stats.create_total_ms;
+            cur.reset();                       // the arena goes back to the cache for the next chain
+            const float t_destroy = ms_since(t0);
+            gg_hmm *nh = nullptr;
+            if (next.valid()) {
+                try { nh = next.get(); } catch (...) { if (rc == GG_OK) throw; }
+            }
+            if (trace)
+                std::fprintf(stderr, "[gg batch] chain %u: device-create %.1f ms, sweep %.1f, fetch %.1f, destroy %.1f, wait-for-next-plan %.1f (its host work %.1f)\n",
+                             i, t_dev, t_sweep - t_dev, t_fetch - t_sweep, t_destroy - t_fetch, ms_since(t0) - t_destroy, host_ms);
+            if (rc != GG_OK) {
+                delete nh;
+                throw CudaError(rc, std::string("chain ") + std::to_string(i) + ": " + e2);
+            }
+            cur.reset(nh);
+        }
+    });
+}
 
 // per-op record of the last timed sweep: kind (OpKind), produced column (EMIT: first column; RUN: first produced column),
 // duration in ms.  Returns the number of ops (may exceed cap).

@@ -111,6 +111,14 @@ typedef struct gg_stats {
 int gg_hmm_run(const gg_problem *p, const gg_options *o, gg_result **out,
                char *err, size_t errlen);
 
+/* ---- many chains (chromosomes) on one device, back to back: what the per-chromosome loop of
+ *      giggles/cli/genotype.py:196-338 does one GenotypeHMM at a time.  The column plan and checkpoint schedule of
+ *      chain i+1 are built on a host thread while the device sweeps chain i.  results[i] is chain i's
+ *      result (caller frees each); on failure the status of the first failing chain is returned, results of the
+ *      chains before it stay valid, the rest are NULL. */
+int gg_hmm_run_batch(const gg_problem *problems, uint32_t n, const gg_options *o, gg_result **results,
+                     char *err, size_t errlen);
+
 /* ---- staged form of the same call, for callers that keep the problem resident
  *      (bench.py times gg_hmm_sweep alone; gg_hmm_run = create+sweep+fetch+destroy). */
 int gg_hmm_create(const gg_problem *p, const gg_options *o, gg_hmm **out,

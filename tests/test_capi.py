@@ -36,6 +36,21 @@ def test_no_cpu_fallback_without_device(have_gpu):
         capi.Hmm(p)
 
 
+def test_batch_reports_errors(have_gpu):
+    good = make_problem(10, 4, coverage=3, max_coverage=3, read_len_mean=1500, seed=1)
+    import copy
+    bad = copy.copy(good)
+    bad.n_alleles = good.n_alleles.copy()
+    bad.n_alleles[2] = 40
+    with pytest.raises(capi.GGError) as ei:
+        capi.hmm_run_batch([bad, good])
+    assert ei.value.status == capi.GG_ERR_INVALID          # a malformed first chain is reported with or without a GPU
+    if not have_gpu:
+        with pytest.raises(capi.GGError) as ei:
+            capi.hmm_run_batch([good, good])
+        assert ei.value.status == capi.GG_ERR_NO_DEVICE
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "giggles_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -140,6 +140,18 @@ def test_fp32_underflow_falls_back_to_fp64_state():
     assert np.abs(got - want).max() <= 1e-11
 
 
+def test_batch_of_chains_matches_single_runs():
+    # gg_hmm_run_batch: chromosomes back to back, planning of chain i+1 overlapped with the sweep of chain i
+    probs = [make_problem(30 + 11 * i, [12, 88, 10, 36][i % 4], coverage=5, max_coverage=4 + i % 3, read_len_mean=1500,
+                          tags=["none", "all", "mixed"][i % 3], seed=300 + i, window=bool(i % 2)) for i in range(6)]
+    singles = [capi.hmm_run(p, device=0).values for p in probs]
+    batch = capi.hmm_run_batch(probs, device=0)
+    assert len(batch) == len(probs)
+    for a, b in zip(singles, batch):
+        assert np.array_equal(a, b.values)
+    assert capi.hmm_run_batch([], device=0) == []
+
+
 def test_single_column_and_empty_problem():
     p = make_problem(1, 6, coverage=0.0, seed=3)
     assert_posteriors_close(capi.hmm_run(p, device=0).values, oracle.oracle_run(p))
