@@ -756,7 +756,11 @@ static uint64_t default_budget(const gg_options *o, int device) {
     if (budget == 0) {
         size_t free_b = 0, total_b = 0;
         GG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        budget = (uint64_t)((free_b + g_arena_cache.cached(device)) * 0.9);
+        const uint64_t cached = g_arena_cache.cached(device);
+        budget = (uint64_t)((free_b + cached) * 0.9);
+        // free memory jitters by a few MB between calls; plan for the retired arena when it is about the size the
+        // budget asks for, so that it is reused instead of being freed and allocated again (hundreds of ms at >100 GB)
+        if (cached && budget > cached && cached >= budget - budget / 8) budget = cached;
     }
     return budget;
 }
