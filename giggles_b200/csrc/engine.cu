@@ -353,29 +353,35 @@ struct Engine {
     }
 
     // Pipelined bulk-copy kernel (hmm_tma_kernel.cuh): fp32, R % 4 == 0, R <= 512.
-    static const void *tma_kernel(bool fwd, uint32_t G, int NS, bool mt, int cwt, bool two) {
-#define GG_TMA(GG, NN, MM, CC, TT) if (G == GG && NS == NN && mt == MM && cwt == CC && two == TT) return fwd ? (const void *)step_tma_kernel<true, GG, NN, MM, CC, TT> : (const void *)step_tma_kernel<false, GG, NN, MM, CC, TT>;
-        GG_TMA(1, 1, false, 8, false) GG_TMA(2, 1, false, 8, false) GG_TMA(4, 1, false, 8, false) GG_TMA(8, 1, false, 8, false)
-        GG_TMA(16, 1, false, 8, false) GG_TMA(32, 1, false, 8, false) GG_TMA(32, 1, false, 16, false)
-        GG_TMA(16, 1, false, 8, true) GG_TMA(32, 1, false, 8, true) GG_TMA(32, 1, false, 16, true)
-        GG_TMA(32, 1, true, 0, false) GG_TMA(32, 2, true, 0, false) GG_TMA(32, 4, true, 0, false)
+    static const void *tma_kernel(bool fwd, int V, uint32_t G, int NS, bool mt, int cwt, bool two) {
+#define GG_TMA(VV, GG, NN, MM, CC, TT) if (V == VV && G == GG && NS == NN && mt == MM && cwt == CC && two == TT) return fwd ? (const void *)step_tma_kernel<true, GG, NN, MM, CC, TT, VV> : (const void *)step_tma_kernel<false, GG, NN, MM, CC, TT, VV>;
+        // float4 rows (R % 4 == 0)
+        GG_TMA(4, 1, 1, false, 8, false) GG_TMA(4, 2, 1, false, 8, false) GG_TMA(4, 4, 1, false, 8, false) GG_TMA(4, 8, 1, false, 8, false)
+        GG_TMA(4, 16, 1, false, 8, false) GG_TMA(4, 32, 1, false, 8, false) GG_TMA(4, 32, 1, false, 16, false)
+        GG_TMA(4, 16, 1, false, 8, true) GG_TMA(4, 32, 1, false, 8, true) GG_TMA(4, 32, 1, false, 16, true)
+        GG_TMA(4, 32, 1, true, 0, false) GG_TMA(4, 32, 2, true, 0, false) GG_TMA(4, 32, 4, true, 0, false)
+        // float2 rows (R % 4 == 2, e.g. 94 haplotypes): panels of 34..256
+        GG_TMA(2, 32, 1, false, 8, false) GG_TMA(2, 32, 1, false, 16, false) GG_TMA(2, 32, 1, false, 8, true) GG_TMA(2, 32, 1, false, 16, true)
+        GG_TMA(2, 32, 2, false, 8, false) GG_TMA(2, 32, 2, false, 16, false) GG_TMA(2, 32, 2, false, 8, true) GG_TMA(2, 32, 2, false, 16, true)
+        GG_TMA(2, 32, 2, true, 0, false) GG_TMA(2, 32, 4, true, 0, false)
 #undef GG_TMA
         return nullptr;
     }
 
     static bool try_launch_tma(gg_hmm *h, const StepArgs<T> &a, const ColumnPlan &pco, bool fwd) {
         if (sizeof(T) != 4 || h->kernel_variant == 1 || a.in == nullptr) return false;
-        if (a.R % 4 != 0 || a.R > 512 || h->shape.V != 4) return false;
-        const int NS = h->shape.NS;
+        const int V = h->shape.V, NS = h->shape.NS;
+        if (V < 2 || a.R > 512) return false;
         if (!h->tma_attr_done) {
-            for (uint32_t g = 1; g <= 32; g <<= 1)
-                for (bool f : {false, true})
-                    for (int ns : {1, 2, 4})
-                        for (bool mt : {false, true})
-                            for (int cwt : {0, 8, 16})
-                                for (bool tw : {false, true})
-                                    if (const void *kk = tma_kernel(f, g, ns, mt, cwt, tw))
-                                        GG_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
+            for (int vv : {2, 4})
+                for (uint32_t g = 1; g <= 32; g <<= 1)
+                    for (bool f : {false, true})
+                        for (int ns : {1, 2, 4})
+                            for (bool mt : {false, true})
+                                for (int cwt : {0, 8, 16})
+                                    for (bool tw : {false, true})
+                                        if (const void *kk = tma_kernel(f, vv, g, ns, mt, cwt, tw))
+                                            GG_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
             h->tma_attr_done = true;
         }
         const uint32_t rpi = 32 / a.G;
@@ -384,7 +390,8 @@ struct Engine {
         // geometry search.  Whole block = one tile (R <= 128): two CTAs of 8 consumer warps per SM when the column's
         // footprint fits twice, else one CTA of 16 (same warp count, deeper ring), else one of 8.  Larger R: row tiles
         // of <= ~40 KB, most consumer warps first, >= 3 stages.
-        const bool two_ok = nred == 2 && a.G >= 16 && NS == 1 && a.R <= 128;   // both blocks of the reduce set held in stages
+        // both blocks of a two-block reduce set held in stages (where that kernel variant is compiled)
+        const bool two_ok = nred == 2 && a.R <= 128 && tma_kernel(fwd, V, a.G, NS, false, 8, true) != nullptr;
         struct Pick { uint32_t cw, tr, stages, ctas; int cwt; TmaGeom L; bool ok; } pick{};
         auto fit = [&](uint32_t cw, uint32_t tr, uint32_t lo, uint32_t hi, size_t cap, uint32_t &stages, TmaGeom &L) {
             for (stages = hi; stages >= lo; --stages) {
@@ -393,10 +400,11 @@ struct Engine {
             }
             return false;
         };
-        if (a.R <= 128 && NS == 1) {
+        if (a.R <= 128 && tma_kernel(fwd, V, a.G, NS, false, 8, false)) {
             uint32_t st; TmaGeom L;
             if (h->kernel_variant != 2 && fit(8, a.R, 3, 4, kMaxDynSmemTma2, st, L)) pick = {8, a.R, st, 2, 8, L, true};
-            else if (a.G == 32 && h->kernel_variant != 3 && fit(16, a.R, 3, kTmaMaxStages, kMaxDynSmemTma, st, L)) pick = {16, a.R, st, 1, 16, L, true};
+            else if (tma_kernel(fwd, V, a.G, NS, false, 16, false) && h->kernel_variant != 3 &&
+                     fit(16, a.R, 3, kTmaMaxStages, kMaxDynSmemTma, st, L)) pick = {16, a.R, st, 1, 16, L, true};
             else if (fit(8, a.R, 3, kTmaMaxStages, kMaxDynSmemTma, st, L)) pick = {8, a.R, st, 1, 8, L, true};
         }
         if (!pick.ok && a.G == 32) {
@@ -408,13 +416,13 @@ struct Engine {
                     uint32_t st; TmaGeom L;
                     const uint32_t trc = std::min<uint32_t>(tr, a.R);
                     if (trc < a.R && fit(cw, trc, 3, 6, kMaxDynSmemTma, st, L)) pick = {cw, trc, st, 1, 0, L, true};
-                    if (tr == ngrp) break;
+                    if (tr == ngrp || tr < 2 * ngrp) break;
                 }
                 if (pick.ok) break;
             }
         }
         if (!pick.ok) return false;
-        const void *k = tma_kernel(fwd, a.G, NS, pick.cwt == 0, pick.cwt, two_ok && pick.cwt != 0);
+        const void *k = tma_kernel(fwd, V, a.G, NS, pick.cwt == 0, pick.cwt, two_ok && pick.cwt != 0);
         if (!k) return false;
         const int threads = 32 * (1 + (int)pick.cw);
         auto key = std::make_tuple(k, threads, (size_t)pick.L.total);

@@ -88,6 +88,17 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 __device__ __forceinline__ void consumer_bar(uint32_t nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
+template <int V>
+__device__ __forceinline__ void lds_vec(float (&d)[V], const void *p) {
+    if (V == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); d[0] = t.x; d[1] = t.y; d[V > 2 ? 2 : 0] = t.z; d[V > 3 ? 3 : 0] = t.w; }
+    else { const float2 t = *reinterpret_cast<const float2 *>(p); d[0] = t.x; d[1] = t.y; }
+}
+template <int V>
+__device__ __forceinline__ void st_vec(void *p, const float (&d)[V]) {
+    if (V == 4) *reinterpret_cast<float4 *>(p) = make_float4(d[0], d[1], d[V > 2 ? 2 : 0], d[V > 3 ? 3 : 0]);
+    else *reinterpret_cast<float2 *>(p) = make_float2(d[0], d[1]);
+}
+
 // row metadata, pre-scaled to byte offsets so the row loop does no address arithmetic:
 //   x = byte offset of the row inside its tile ((R1 - row0)*R*4) | valid << 31
 //   y = R1*4 (12 bits) | (allele class of R1 in the output column)*4 << 12 (7 bits) | (... input column)*4 << 19
@@ -100,7 +111,8 @@ __device__ __forceinline__ uint2 pack_row(uint32_t R1, uint32_t row0, uint32_t R
 // column - reduce-set accumulator, many allele classes - does not fit twice); 0 = taken from blockDim.
 // TWO: the reduce set has exactly two blocks and both are held in stages (compile-time so that the common
 // one-block kernels carry none of its code).
-template <bool FWD, int G, int NS, bool MT, int CWT, bool TWO>
+// V: floats per vector access (4: R % 4 == 0; 2: R % 4 == 2, e.g. a 47-sample / 94-haplotype panel).
+template <bool FWD, int G, int NS, bool MT, int CWT, bool TWO, int V>
 __global__ void __launch_bounds__(32 * (1 + (CWT ? CWT : kTmaMaxConsumerWarps)), (CWT == 8 ? 2 : 1))
 step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t TR_arg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -268,25 +280,25 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
 
     const float inv = (float)(1.0 / *a.in_scale);
     const float cA = (float)a.tA * inv, cB = (float)a.tB * inv, cC = (float)a.tC * inv;
-    // this lane's columns: NS groups of 4; idle slots shadow columns 0..3 with zero weight and no stores
+    // this lane's columns: NS groups of V; idle slots shadow the first columns with zero weight and no stores
     bool cok[NS];
     uint32_t ccol[NS];
-    uint32_t a2o[NS][4], a2i[NS][4];
+    uint32_t a2o[NS][V], a2i[NS][V];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-        cok[s] = (s * G + gl) * 4 < R;
-        ccol[s] = cok[s] ? (s * G + gl) * 4 : 0u;
+        cok[s] = (s * G + gl) * V < R;
+        ccol[s] = cok[s] ? (s * G + gl) * V : 0u;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < V; ++v) {
             a2o[s][v] = cok[s] ? s_al_o[ccol[s] + v] : 0u;
             a2i[s][v] = cok[s] ? s_al_i[ccol[s] + v] : 0u;
         }
     }
-    float qc[NS][4];
+    float qc[NS][V];
 #pragma unroll
     for (int s = 0; s < NS; ++s)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) qc[s][v] = 0.f;
+        for (int v = 0; v < V; ++v) qc[s][v] = 0.f;
     uint32_t cur_cls = 0xffffffffu;
     float cta_sum = 0.f, sacc = 0.f;
     uint32_t seq = 0, parity_item = 0;
@@ -295,16 +307,17 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
 #pragma unroll
         for (int s = 0; s < NS; ++s)
             if (cok[s]) {
-                float4 *qd = reinterpret_cast<float4 *>(s_q + (grp * NCo + (cur_cls >> 2)) * Rp + ccol[s]);
-                float4 o = *qd;
-                o.x += qc[s][0]; o.y += qc[s][1]; o.z += qc[s][2]; o.w += qc[s][3];
-                *qd = o;
-                qc[s][0] = qc[s][1] = qc[s][2] = qc[s][3] = 0.f;
+                float *qd = s_q + (grp * NCo + (cur_cls >> 2)) * Rp + ccol[s];
+                float o[V];
+                lds_vec<V>(o, qd);
+#pragma unroll
+                for (int v = 0; v < V; ++v) { o[v] += qc[s][v]; qc[s][v] = 0.f; }
+                st_vec<V>(qd, o);
             }
     };
 
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, parity_item ^= 1u) {
-        float kx[NS][4], kx1[NS][4], kr[NS][4], kc[NS][4], gout[NS][4], colacc[NS][4];
+        float kx[NS][V], kx1[NS][V], kr[NS][V], kc[NS][V], gout[NS][V], colacc[NS][V];
         float totacc = 0.f, totv = 0.f;
         const float *fgo = nullptr, *fgi = nullptr;
         float *outp = nullptr;
@@ -329,11 +342,11 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                     const unsigned char *stb = smem_raw + L.off_stage + sk * L.stage_bytes;
                     const float *st = reinterpret_cast<const float *>(stb);
                     const float *fgk = s_meta[sk].fg_self;
-                    float gk[NS][4];
+                    float gk[NS][V];
 #pragma unroll
                     for (int s = 0; s < NS; ++s)
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) gk[s][v] = FWD ? 1.f : fgk[NCi + a2i[s][v]];
+                        for (int v = 0; v < V; ++v) gk[s][v] = FWD ? 1.f : fgk[NCi + a2i[s][v]];
                     for (uint32_t it = 0; it < L.n_iter_t; ++it) {
                         const uint32_t rl = it * ngrp + grp;     // row inside the tile, natural order
                         if (rl < rows) {
@@ -341,19 +354,20 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
 #pragma unroll
                             for (int s = 0; s < NS; ++s)
                                 if (cok[s]) {
-                                    float4 v = *reinterpret_cast<const float4 *>(st + rl * R + ccol[s]);
+                                    float xv[V];
+                                    lds_vec<V>(xv, st + rl * R + ccol[s]);
                                     if (!FWD) {
-                                        v.x *= fk * gk[s][0];
-                                        v.y *= fk * gk[s][1];
-                                        v.z *= fk * gk[s][2];
-                                        v.w *= fk * gk[s][3];
+#pragma unroll
+                                        for (int v = 0; v < V; ++v) xv[v] *= fk * gk[s][v];
                                     }
-                                    float4 *dst = reinterpret_cast<float4 *>(s_acc + rl * R + ccol[s]);
+                                    float *dst = s_acc + rl * R + ccol[s];
                                     if (k > 0) {
-                                        const float4 o = *dst;
-                                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                                        float o[V];
+                                        lds_vec<V>(o, dst);
+#pragma unroll
+                                        for (int v = 0; v < V; ++v) xv[v] += o[v];
                                     }
-                                    *dst = v;
+                                    st_vec<V>(dst, xv);
                                 }
                         }
                     }
@@ -408,7 +422,7 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
 #pragma unroll
                 for (int s = 0; s < NS; ++s)
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
+                    for (int v = 0; v < V; ++v) {
                         const float cb = cB * (side[R + ccol[s] + v] + (two ? side1[R + ccol[s] + v] : 0.f)) + ctot;
                         gout[s][v] = fgo[NCo + a2o[s][v]];
                         kx1[s][v] = (two && !FWD) ? cA * m1->fg_self[NCi + a2i[s][v]] : 0.f;
@@ -459,18 +473,23 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                 float rs = 0.f;
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
-                    const float4 xv = *reinterpret_cast<const float4 *>(xcolp[s] + rowb);
-                    float x[4] = {xv.x, xv.y, xv.z, xv.w};
-                    float x1[4] = {0.f, 0.f, 0.f, 0.f};
+                    float x[V], x1[V];
+                    lds_vec<V>(x, xcolp[s] + rowb);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) x1[v] = 0.f;
                     if (two) {
-                        const float4 yv = *reinterpret_cast<const float4 *>(xcolp1[s] + rowb);
-                        if (FWD) { x[0] += yv.x; x[1] += yv.y; x[2] += yv.z; x[3] += yv.w; }
-                        else { x1[0] = fk1 * yv.x; x1[1] = fk1 * yv.y; x1[2] = fk1 * yv.z; x1[3] = fk1 * yv.w; }
+                        float y[V];
+                        lds_vec<V>(y, xcolp1[s] + rowb);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            if (FWD) x[v] += y[v];
+                            else x1[v] = fk1 * y[v];
+                        }
                     }
-                    float o[4];
+                    float o[V];
                     if (FWD) {
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
+                        for (int v = 0; v < V; ++v) {
                             o[v] = fo * fmaf(kx[s][v], x[v], fmaf(kr[s][v], rowterm, kc[s][v]));
                             rs += o[v];
                             colacc[s][v] += o[v];
@@ -478,18 +497,19 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                     } else {
                         float dot = 0.f;
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
+                        for (int v = 0; v < V; ++v) {
                             o[v] = fmaf(kx[s][v], fk * x[v], fmaf(kx1[s][v], x1[v], rowterm + kc[s][v]));
                             dot = fmaf(o[v], gout[s][v], dot);
                             colacc[s][v] = fmaf(fo, o[v], colacc[s][v]);      // times gout once per block, below
                         }
                         rs = fmaf(fo, dot, rs);
                     }
-                    if (rvalid && cok[s]) *reinterpret_cast<float4 *>(ocolp[s] + rowb) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (rvalid && cok[s]) st_vec<V>(ocolp[s] + rowb, o);
                     if (FWD) {
-                        const float4 bv = *reinterpret_cast<const float4 *>(bcolp[s] + rowb);
-                        qc[s][0] = fmaf(o[0], bv.x, qc[s][0]); qc[s][1] = fmaf(o[1], bv.y, qc[s][1]);
-                        qc[s][2] = fmaf(o[2], bv.z, qc[s][2]); qc[s][3] = fmaf(o[3], bv.w, qc[s][3]);
+                        float bv[V];
+                        lds_vec<V>(bv, bcolp[s] + rowb);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) qc[s][v] = fmaf(o[v], bv[v], qc[s][v]);
                     }
                 }
 #pragma unroll
@@ -517,9 +537,9 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
         for (int s = 0; s < NS; ++s) {
             if (!FWD) {
 #pragma unroll
-                for (int v = 0; v < 4; ++v) colacc[s][v] *= gout[s][v];
+                for (int v = 0; v < V; ++v) colacc[s][v] *= gout[s][v];
             }
-            if (cok[s]) *reinterpret_cast<float4 *>(cr + grp * Rp + ccol[s]) = make_float4(colacc[s][0], colacc[s][1], colacc[s][2], colacc[s][3]);
+            if (cok[s]) st_vec<V>(cr + grp * Rp + ccol[s], colacc[s]);
         }
         if (gl == 0) tr[grp] = totacc;
         consumer_bar(nct);

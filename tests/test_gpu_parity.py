@@ -61,6 +61,8 @@ CASES = [
     dict(n_columns=30, n_haps=128, coverage=6, max_coverage=4, read_len_mean=900, tags="mixed"),
     dict(n_columns=12, n_haps=4, coverage=3, max_coverage=3, read_len_mean=1500),
     dict(n_columns=200, n_haps=10, region_bp=40000, coverage=10, max_coverage=10),
+    dict(n_columns=30, n_haps=94, coverage=10, max_coverage=6, read_len_mean=800, multiallelic_frac=0.3, max_alleles=8),   # R % 4 == 2
+    dict(n_columns=12, n_haps=130, coverage=8, max_coverage=4, read_len_mean=500, multiallelic_frac=0.5),
 ]
 
 
@@ -85,7 +87,7 @@ def test_randomized_campaign_all_kernel_families():
     rng = np.random.default_rng(2024)
     done = 0
     while done < 48:
-        R = int(rng.choice([4, 6, 9, 10, 12, 16, 24, 33, 36, 64, 88, 128, 132, 200, 256, 400]))
+        R = int(rng.choice([4, 6, 9, 10, 12, 16, 24, 33, 34, 36, 64, 66, 88, 94, 128, 130, 132, 200, 254, 256, 400]))
         max_cov = int(rng.integers(0, 8))
         while (1 << max_cov) * R * R > (2e6 if R <= 128 else 4e6) and max_cov > 0:
             max_cov -= 1

@@ -28,6 +28,12 @@ cases = [
     dict(n_columns=12, n_haps=256, coverage=8, max_coverage=4, read_len_mean=500, tags="mixed", multiallelic_frac=0.3),
     dict(n_columns=12, n_haps=132, coverage=8, max_coverage=4, read_len_mean=500, missing_frac=0.03),
     dict(n_columns=8, n_haps=512, coverage=4, max_coverage=2, read_len_mean=600),
+    dict(n_columns=30, n_haps=94, coverage=10, max_coverage=6, read_len_mean=800, multiallelic_frac=0.3, max_alleles=8),
+    dict(n_columns=30, n_haps=94, coverage=8, max_coverage=5, read_len_mean=600, tags="mixed", window=True),
+    dict(n_columns=20, n_haps=34, coverage=8, max_coverage=6, read_len_mean=800),
+    dict(n_columns=20, n_haps=66, coverage=8, max_coverage=6, read_len_mean=800, missing_frac=0.05),
+    dict(n_columns=12, n_haps=130, coverage=8, max_coverage=4, read_len_mean=500, multiallelic_frac=0.5),
+    dict(n_columns=10, n_haps=254, coverage=6, max_coverage=3, read_len_mean=500, tags="mixed"),
 ]
 worst = 0.0
 for i, kw in enumerate(cases):

@@ -33,6 +33,9 @@ if "r400" in which:
     run("cfg5 R=400 mc=6 C=24", config5_window(24, max_coverage=6))
     run("cfg5 R=400 mc=6 C=24 generic", config5_window(24, max_coverage=6), kv=1)
     run("R=256 biallelic mc=8 C=24", config2_window(24, max_coverage=8, n_haps=256))
+if "r94" in which:
+    run("R=94 mc=15 C=48", config2_window(48, max_coverage=15, n_haps=94))
+    run("R=94 mc=15 C=48 generic", config2_window(48, max_coverage=15, n_haps=94), kv=1)
 if "big" in which:
     run("cfg2 mc=15 C=48", config2_window(48, max_coverage=15))
     run("cfg2 mc=15 C=160 (checkpointed)", config2_window(160, max_coverage=15), reps=1)
