@@ -45,7 +45,12 @@ void build_plan(const gg_problem &p, Plan &pl) {
             "gg_problem: read arrays missing");
     pl = Plan();
     pl.n_columns = C;
-    pl.n_haps = R;
+    // An odd panel is laid out with one phantom haplotype whose allele is missing at every column: its states have
+    // emission 0, so they carry no mass in either direction and change no sum, but rows stay 8-byte aligned and the
+    // vectorised kernels apply.  The transition keeps the true haplotype count (TransitionProbabilityComputer's s).
+    const uint32_t RL = R + (R & 1u);
+    pl.n_haps = RL;
+    pl.n_haps_true = R;
     pl.n_reads = N;
     if (p.positions)
         for (uint32_t c = 1; c < C; ++c)
@@ -71,8 +76,8 @@ void build_plan(const gg_problem &p, Plan &pl) {
     pl.active_off.assign(C + 1, 0);
     pl.untagged_off.assign(C + 1, 0);
     pl.gl_offsets.assign(C + 1, 0);
-    pl.allele1.resize((size_t)C * R);
-    pl.row_order.resize((size_t)C * R);
+    pl.allele1.assign((size_t)C * RL, 0);
+    pl.row_order.resize((size_t)C * RL);
 
     std::vector<uint32_t> active, next_active, cursor(N, 0), prev_untagged, untagged;
     for (uint32_t k = 0; k < N; ++k) cursor[k] = p.read_entry_offset[k];
@@ -90,15 +95,15 @@ void build_plan(const gg_problem &p, Plan &pl) {
         for (uint32_t h = 0; h < R; ++h) {
             int32_t a = p.allele_ref[(size_t)c * R + h];
             require(a >= -1 && a < (int32_t)nA, "gg_problem: allele_ref out of range");
-            pl.allele1[(size_t)c * R + h] = (uint8_t)(a + 1);
+            pl.allele1[(size_t)c * RL + h] = (uint8_t)(a + 1);
         }
         // stable counting sort of the haplotypes by allele class (<= 17 classes)
-        const uint8_t *al = &pl.allele1[(size_t)c * R];
+        const uint8_t *al = &pl.allele1[(size_t)c * RL];
         uint32_t cnt[GG_MAX_ALLELES + 2] = {0};
-        for (uint32_t h = 0; h < R; ++h) ++cnt[al[h] + 1];
+        for (uint32_t h = 0; h < RL; ++h) ++cnt[al[h] + 1];
         for (uint32_t k = 1; k <= GG_MAX_ALLELES + 1; ++k) cnt[k] += cnt[k - 1];
-        uint16_t *ro = &pl.row_order[(size_t)c * R];
-        for (uint32_t h = 0; h < R; ++h) ro[cnt[al[h]]++] = (uint16_t)h;
+        uint16_t *ro = &pl.row_order[(size_t)c * RL];
+        for (uint32_t h = 0; h < RL; ++h) ro[cnt[al[h]]++] = (uint16_t)h;
 
         // active set: keep spanning reads (in id order), append reads starting here
         next_active.clear();

@@ -42,7 +42,8 @@ struct ColumnPlan {
 };
 
 struct Plan {
-    uint32_t n_columns = 0, n_haps = 0, n_reads = 0;
+    uint32_t n_columns = 0, n_haps = 0, n_reads = 0;   // n_haps: LAYOUT width (even: an odd panel gets one phantom haplotype)
+    uint32_t n_haps_true = 0;                          // the panel's haplotype count
     std::vector<ColumnPlan> cols;
     // CSR of active / untagged read ids per column (for the structure parity test)
     std::vector<uint64_t> active_off, untagged_off;

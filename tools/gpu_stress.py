@@ -14,7 +14,7 @@ t0 = time.time()
 n = bad = 0
 worst = 0.0
 while time.time() - t0 < budget_s:
-    R = int(rng.choice([4, 6, 8, 9, 10, 12, 16, 20, 24, 32, 33, 34, 36, 48, 50, 64, 66, 88, 94, 96, 126, 128, 130, 132, 160, 200, 254, 256, 400]))
+    R = int(rng.choice([4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 20, 24, 31, 32, 33, 34, 87, 95, 127, 129, 36, 48, 50, 64, 66, 88, 94, 96, 126, 128, 130, 132, 160, 200, 254, 256, 400]))
     cap_states = 3e6 if R <= 128 else 6e6
     max_cov = int(rng.integers(0, 9))
     while (1 << max_cov) * R * R > cap_states and max_cov > 0:
