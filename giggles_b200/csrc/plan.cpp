@@ -37,7 +37,7 @@ static void require(bool ok, const char *msg) {
 void build_plan(const gg_problem &p, Plan &pl) {
     const uint32_t C = p.n_columns, R = p.n_haps, N = p.n_reads;
     require(R >= 1, "gg_problem: n_haps must be >= 1");
-    require(R <= 1024, "gg_problem: n_haps > 1024 is not supported");
+    require(R <= 1020, "gg_problem: n_haps > 1020 is not supported");
     require(C == 0 || (p.n_alleles && p.allele_ref), "gg_problem: n_alleles / allele_ref missing");
     require(C <= 1 || p.recomb, "gg_problem: recomb missing");
     require(N == 0 || (p.read_tag && p.read_entry_offset && p.entry_column && p.entry_allele &&
@@ -45,10 +45,10 @@ void build_plan(const gg_problem &p, Plan &pl) {
             "gg_problem: read arrays missing");
     pl = Plan();
     pl.n_columns = C;
-    // An odd panel is laid out with one phantom haplotype whose allele is missing at every column: its states have
+    // An odd panel is laid out with phantom haplotypes (one; up to three above 256) whose allele is missing at every column: their states have
     // emission 0, so they carry no mass in either direction and change no sum, but rows stay 8-byte aligned and the
     // vectorised kernels apply.  The transition keeps the true haplotype count (TransitionProbabilityComputer's s).
-    const uint32_t RL = R + (R & 1u);
+    const uint32_t RL = R > 256 ? ((R + 3u) & ~3u) : R + (R & 1u);   // > 256: pad to a multiple of 4 (float4 tiles)
     pl.n_haps = RL;
     pl.n_haps_true = R;
     pl.n_reads = N;
