@@ -552,6 +552,7 @@ struct Engine {
         a.R = R;
         a.BS = (uint32_t)block_stride(R);
         a.max_classes = run.max_classes;
+        a.no_fast_posterior = h->kernel_variant == 6;
         const void *k = chain_kernel_ptr(run.fwd, (R + kChainWarps - 1) / kChainWarps);
         const uint32_t smem = chain_smem_bytes(R, run.max_classes, run.fwd);
         if (!h->chain_attr_done) {

@@ -41,6 +41,7 @@ struct ChainArgs {
     double *result;
     const uint8_t *allele1;   // [C][R] panel alleles + 1
     uint32_t R, BS, max_classes;
+    uint32_t no_fast_posterior;   // A/B switch: always use the shared-memory posterior path
 };
 
 struct ChainParams {          // per-step parameters staged in shared memory one step ahead
@@ -59,6 +60,7 @@ __host__ __device__ inline uint32_t chain_smem_bytes(uint32_t R, uint32_t ncls, 
         o += kChainWarps * ncls * Rp * 4;   // posterior partials per warp and row class
         o += ncls * Rp * 4;                 // folded
         o += kMaxClasses * kMaxClasses * 4; // W[i][j]
+        o += kChainWarps * 4 * 4;           // bi-allelic fast path: per-warp W partials
     }
     return (o + 127u) & ~127u;
 }
@@ -79,6 +81,7 @@ chain_kernel(const ChainArgs a) {
     float *s_Q = s_tot + 4;
     float *s_Qf = s_Q + (FWD ? kChainWarps * NCmax * Rp : 0);
     float *s_W = s_Qf + (FWD ? NCmax * Rp : 0);
+    float *s_Wp = s_W + kMaxClasses * kMaxClasses;
 
     const bool cok = lane * 4 < R;
     const uint32_t ccol = cok ? lane * 4 : 0u;
@@ -196,6 +199,7 @@ chain_kernel(const ChainArgs a) {
         if (k % kChainChunk == 0 && k > 0) load_chunk(k / kChainChunk + 1);   // the chunk after next; its buffer was last read in step k-1
         float *outp = reinterpret_cast<float *>(a.arena + st.out_off);
         const bool have_prev = FWD ? (k > 0 || has_in) : true;
+        const bool fast = FWD && NCo == 3 && !a.no_fast_posterior;
         uint32_t a2o[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) a2o[q] = cok ? p->al_out[ccol + q] : 0u;
@@ -211,10 +215,14 @@ chain_kernel(const ChainArgs a) {
                 g[q] = p->G_out[a2o[q]];
                 cb[q] = cB * colM[q] + cC * totM;
             }
-            // zero this warp's posterior partials
-            for (uint32_t z = lane; z < NCo * (Rp >> 2); z += 32)
-                reinterpret_cast<float4 *>(s_Q + warp * NCmax * Rp)[z] = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncwarp();
+            // posterior partials.  Bi-allelic columns (the common case): two register accumulators per lane and row
+            // class, binned by column class with four warp reductions.  Otherwise: per-warp shared-memory partials.
+            float acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+            if (!fast) {
+                for (uint32_t z = lane; z < NCo * (Rp >> 2); z += 32)
+                    reinterpret_cast<float4 *>(s_Q + warp * NCmax * Rp)[z] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+            }
 #pragma unroll
             for (int i = 0; i < NIT; ++i) {
                 const uint32_t a1 = p->al_out[rows[i]];
@@ -231,12 +239,33 @@ chain_kernel(const ChainArgs a) {
                 for (int sh = 16; sh > 0; sh >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, sh);
                 rsum[i] = rs;
                 tpart += rs;
-                if (rok[i] && cok) {
+                if (fast) {
+                    if (a1 == 1) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc1[q] = fmaf(v[i][q], bnext[i][q], acc1[q]);
+                    } else {           // class 2, or a missing allele / idle row slot whose alpha is 0
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc2[q] = fmaf(v[i][q], bnext[i][q], acc2[q]);
+                    }
+                } else if (rok[i] && cok) {
                     float4 *qd = reinterpret_cast<float4 *>(s_Q + (warp * NCmax + a1) * Rp + ccol);
                     float4 acc = *qd;
                     acc.x = fmaf(v[i][0], bnext[i][0], acc.x); acc.y = fmaf(v[i][1], bnext[i][1], acc.y);
                     acc.z = fmaf(v[i][2], bnext[i][2], acc.z); acc.w = fmaf(v[i][3], bnext[i][3], acc.w);
                     *qd = acc;
+                }
+            }
+            if (fast) {
+                float w4[4] = {0.f, 0.f, 0.f, 0.f};       // (row class, column class) = (1,1) (1,2) (2,1) (2,2)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    w4[0] += a2o[q] == 1 ? acc1[q] : 0.f; w4[1] += a2o[q] == 2 ? acc1[q] : 0.f;
+                    w4[2] += a2o[q] == 1 ? acc2[q] : 0.f; w4[3] += a2o[q] == 2 ? acc2[q] : 0.f;
+                }
+#pragma unroll
+                for (int z = 0; z < 4; ++z) {
+                    for (int sh = 16; sh > 0; sh >>= 1) w4[z] += __shfl_xor_sync(0xffffffffu, w4[z], sh);
+                    if (lane == 0) s_Wp[warp * 4 + z] = w4[z];
                 }
             }
             prefetch_beta(k + 1);      // beta of the next column: in flight across the barriers below
@@ -277,7 +306,14 @@ chain_kernel(const ChainArgs a) {
             for (int w = 0; w < kChainWarps; ++w) ts += s_totp[w];
             s_tot[par] = ts;
         }
-        if (FWD) {
+        if (FWD && fast) {
+            if (tid < 4) {
+                float q = 0.f;
+#pragma unroll
+                for (int w = 0; w < kChainWarps; ++w) q += s_Wp[w * 4 + tid];
+                s_W[(1 + (tid >> 1)) * 3 + 1 + (tid & 1)] = q;
+            }
+        } else if (FWD) {
             for (uint32_t idx = tid; idx < NCo * R; idx += kChainThreads) {
                 const uint32_t cls = idx / R, t = idx % R;
                 float q = 0.f;
@@ -313,6 +349,7 @@ chain_kernel(const ChainArgs a) {
                 if (tid == 0) outp[RR + 2 * R] = tot;
             }
             // W[i][j] = sum over columns of class j of the folded posterior partials; one warp per pair
+            if (!fast) {
             for (uint32_t pr = warp; pr < NCo * NCo; pr += kChainWarps) {
                 const uint32_t ci = pr / NCo, cj = pr % NCo;
                 float w = 0.f;
@@ -322,6 +359,7 @@ chain_kernel(const ChainArgs a) {
                 if (lane == 0) s_W[pr] = w;
             }
             __syncthreads();                               // B3
+            }
             if (warp == 0) {
                 const uint32_t nA = st.nA_out, ng = nA * (nA + 1) / 2;
                 double norm = 0.0;

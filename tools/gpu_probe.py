@@ -25,6 +25,10 @@ which = sys.argv[1:] or ["small", "mid", "big"]
 if "small" in which:
     run("cfg1 R=10 C=2000", config1(n_columns=2000))
     run("cfg2 tagged R=88 C=2000", config2_window(2000, tags="all"))
+if "tagged" in which:
+    for _ in range(2):
+        run("tagged R=88 C=4000 fast", config2_window(4000, tags="all"))
+        run("tagged R=88 C=4000 smem-posterior", config2_window(4000, tags="all"), kv=6)
 if "mid" in which:
     run("cfg2 mc=10 C=64", config2_window(64, max_coverage=10))
     run("cfg2 mc=12 C=64", config2_window(64, max_coverage=12))
