@@ -315,19 +315,16 @@ struct Engine {
     }
 
     // Warp-per-block kernel for small panels (hmm_warp_kernel.cuh): fp32, R <= 32.
-    static const void *warp_kernel(bool fwd, int V, uint32_t ni) {
-#define GG_WK(VV, NN) if (V == VV && ni == NN) return fwd ? (const void *)step_warp_kernel<VV, NN, true> : (const void *)step_warp_kernel<VV, NN, false>;
-        GG_WK(1, 2) GG_WK(1, 4) GG_WK(1, 8) GG_WK(2, 2) GG_WK(2, 4) GG_WK(2, 8) GG_WK(2, 16) GG_WK(4, 2) GG_WK(4, 4) GG_WK(4, 8)
+    static const void *warp_kernel(bool fwd, int V, uint32_t G) {
+#define GG_WK(VV, GG) if (V == VV && G == GG) return fwd ? (const void *)step_warp_kernel<VV, GG, true> : (const void *)step_warp_kernel<VV, GG, false>;
+        GG_WK(2, 1) GG_WK(2, 2) GG_WK(2, 4) GG_WK(2, 8) GG_WK(2, 16) GG_WK(4, 1) GG_WK(4, 2) GG_WK(4, 4) GG_WK(4, 8)
 #undef GG_WK
         return nullptr;
     }
 
     static bool try_launch_warp(gg_hmm *h, const StepArgs<T> &a, const ColumnPlan &pco, bool fwd) {
         if (sizeof(T) != 4 || h->kernel_variant == 1 || h->kernel_variant == 5 || a.in == nullptr || a.R > 32) return false;
-        const uint32_t rpi = 32 / a.G;
-        const uint32_t n_iter = (a.R + rpi - 1) / rpi;
-        const uint32_t ni = std::max<uint32_t>(2, pow2ceil(n_iter));
-        const void *k = warp_kernel(fwd, h->shape.V, ni);
+        const void *k = warp_kernel(fwd, h->shape.V, a.G);
         if (!k) return false;
         const size_t smem = fwd ? (size_t)kWarpKernelWarps * a.R * a.R * sizeof(float) : 16;
         const int threads = 32 * kWarpKernelWarps;

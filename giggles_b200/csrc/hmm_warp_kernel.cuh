@@ -14,19 +14,20 @@ namespace gg {
 
 constexpr int kWarpKernelWarps = 8;
 
-template <int V, int NI, bool FWD>
+template <int V, int G, bool FWD>
 __global__ void __launch_bounds__(32 * kWarpKernelWarps)
 step_warp_kernel(const StepArgs<float> a) {
     typedef float T;
+    constexpr int NI = (V * G * G / 32) > 0 ? (V * G * G / 32) : 1;     // row iterations: ceil(R / (32/G)) for R <= V*G
     extern __shared__ __align__(16) float s_pos[];      // forward: [warps][R*R] per-position posterior accumulators
     __shared__ float s_sum[kWarpKernelWarps];
     __shared__ double s_W[kPartialStride];
     __shared__ double s_L[GG_MAX_ALLELES * (GG_MAX_ALLELES + 1) / 2];
     __shared__ bool s_last;
 
-    const uint32_t R = a.R, G = a.G;
+    const uint32_t R = a.R;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t rpi = 32u / G;
+    constexpr uint32_t rpi = 32u / G;
     const uint32_t sub = lane / G, gl = lane % G;
     const uint32_t NCo = a.nA_out + 1, NCi = a.nA_in + 1;
     const uint32_t fgs_o = 2 * NCo, fgs_i = 2 * NCi;
@@ -49,13 +50,14 @@ step_warp_kernel(const StepArgs<float> a) {
         a2i[v] = (cok && has_in) ? a.al_in[ccol + v] : 0u;
     }
     // per row slot: row index and its allele classes (fixed for the whole kernel)
-    uint32_t rowi[NI], a1o[NI], a1i[NI];
+    uint32_t rowi[NI], rowoff[NI], a1o[NI], a1i[NI];
     bool rok[NI];
 #pragma unroll
     for (int it = 0; it < NI; ++it) {
         const uint32_t r = it * rpi + sub;
         rok[it] = (uint32_t)it < n_iter && r < R;
         rowi[it] = rok[it] ? r : 0u;
+        rowoff[it] = rowi[it] * R;
         a1o[it] = rok[it] ? a.al_out[rowi[it]] : 0u;
         a1i[it] = (rok[it] && has_in) ? a.al_in[rowi[it]] : 0u;
     }
@@ -93,6 +95,64 @@ step_warp_kernel(const StepArgs<float> a) {
             gout[v] = fgo[NCo + a2o[v]];
             gin0[v] = (!FWD && has_in) ? a.fg_in[(uint64_t)b_in0 * fgs_i + NCi + a2i[v]] : 1.f;
         }
+        float *outp = a.out + (uint64_t)b_out * BS;
+        float totacc = 0.f;
+        if (nred == 1) {
+            // ---- fast path (no read starts or ends between the columns): one input block, straight-line code
+            const float *blk = a.in + (uint64_t)b_in0 * BS;
+            const float *bblk = FWD ? a.beta + (uint64_t)b_out * BS : blk;
+            const float *fgi = FWD ? fgo : a.fg_in + (uint64_t)b_in0 * fgs_i;
+            load_vec<float, V>(colv, blk + (uint32_t)o_col + ccol);
+            totv = blk[(uint32_t)o_tot];
+            float kc[V], kx[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                kc[v] = fmaf(cB, colv[v], cC * totv);
+                kx[v] = FWD ? cA : cA * gin0[v];
+            }
+            constexpr int CH = NI < 4 ? NI : 4;        // rows whose loads are issued together
+#pragma unroll
+            for (int c0 = 0; c0 < NI; c0 += CH) {
+                float xin[CH][V], bin[CH][V], rowin[CH], fo_r[CH], fk_r[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int it = c0 + j;
+                    load_vec<float, V>(xin[j], blk + rowoff[it] + ccol);
+                    if (FWD) load_vec<float, V>(bin[j], bblk + rowoff[it] + ccol);
+                    rowin[j] = blk[(uint32_t)o_row + rowi[it]];
+                    fo_r[j] = fgo[a1o[it]];
+                    fk_r[j] = FWD ? 1.f : fgi[a1i[it]];
+                }
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int it = c0 + j;
+                    const bool live = rok[it] && cok;
+                    const float rowterm = cB * rowin[j];
+                    float o[V], rs = 0.f;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const float base = fmaf(kx[v], fk_r[j] * xin[j][v], rowterm + kc[v]);
+                        float w;
+                        if (FWD) {
+                            o[v] = (fo_r[j] * gout[v]) * base;
+                            w = o[v];
+                            qa[it][v] = fmaf(live ? o[v] : 0.f, bin[j][v], qa[it][v]);
+                        } else {
+                            o[v] = (a1o[it] != 0 && a2o[v] != 0) ? base : 0.f;
+                            w = o[v] * (fo_r[j] * gout[v]);
+                        }
+                        w = live ? w : 0.f;
+                        rs += w;
+                        colacc[v] += w;
+                    }
+                    if (live) store_vec<float, V>(outp + rowoff[it] + ccol, o);
+#pragma unroll
+                    for (int s = G >> 1; s > 0; s >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, s);
+                    if (gl == 0 && rok[it]) outp[(uint32_t)o_row + rowi[it]] = rs;
+                    totacc += rs;
+                }
+            }
+        } else {
         if (has_in) {
             uint32_t subm = 0;
             for (uint32_t k = 0; k < nred; ++k) {
@@ -105,8 +165,6 @@ step_warp_kernel(const StepArgs<float> a) {
             }
         }
         const float ctot = cC * totv;
-        float *outp = a.out + (uint64_t)b_out * BS;
-        float totacc = 0.f;
 #pragma unroll
         for (int it = 0; it < NI; ++it) {
             if ((uint32_t)it < n_iter) {       // warp-uniform
@@ -162,13 +220,16 @@ step_warp_kernel(const StepArgs<float> a) {
                         for (int v = 0; v < V; ++v) qa[it][v] = fmaf(o[v], bv[v], qa[it][v]);
                     }
                 }
-                for (uint32_t s = G >> 1; s; s >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, s);
+#pragma unroll
+                for (int s = G >> 1; s > 0; s >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, s);
                 if (gl == 0 && rok[it]) outp[o_row + R1] = rs;
                 totacc += rs;
             }
         }
+        }
         // column sums / totals across the row groups of the warp
-        for (uint32_t s = G; s < 32; s <<= 1) {
+#pragma unroll
+        for (int s = G; s < 32; s <<= 1) {
 #pragma unroll
             for (int v = 0; v < V; ++v) colacc[v] += __shfl_xor_sync(0xffffffffu, colacc[v], s);
             totacc += __shfl_xor_sync(0xffffffffu, totacc, s);
