@@ -16,6 +16,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -112,6 +113,14 @@ struct ArenaCache {
 };
 static ArenaCache g_arena_cache;
 
+// cudaFuncSetAttribute is per device: remember which (device, kernel family) pairs have been configured
+static bool first_time_on_device(int device, int family) {
+    static std::mutex mu;
+    static std::set<std::pair<int, int>> seen;
+    std::lock_guard<std::mutex> g(mu);
+    return seen.insert({device, family}).second;
+}
+
 struct LaunchShape {
     int V, NS;
     uint32_t G, nwarps_fwd, nwarps_bwd;
@@ -126,7 +135,6 @@ struct gg_hmm {
     Schedule sched;
     bool fp64 = false;
     int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined, never two CTAs per SM, 3 = pipelined, never 16 consumer warps, 4 = no chain kernel, 5 = no warp-per-block kernel
-    bool tma_attr_done = false, chain_attr_done = false;
     int device = 0;
     int num_sms = 0;
     size_t elem = 4;
@@ -369,7 +377,7 @@ struct Engine {
         if (sizeof(T) != 4 || h->kernel_variant == 1 || a.in == nullptr) return false;
         const int V = h->shape.V, NS = h->shape.NS;
         if (V < 2 || a.R > 512) return false;
-        if (!h->tma_attr_done) {
+        if (first_time_on_device(h->device, 1)) {
             for (int vv : {2, 4})
                 for (uint32_t g = 1; g <= 32; g <<= 1)
                     for (bool f : {false, true})
@@ -379,7 +387,6 @@ struct Engine {
                                     for (bool tw : {false, true})
                                         if (const void *kk = tma_kernel(f, vv, g, ns, mt, cwt, tw))
                                             GG_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
-            h->tma_attr_done = true;
         }
         const uint32_t rpi = 32 / a.G;
         const uint32_t nred = fwd ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
@@ -552,20 +559,18 @@ struct Engine {
         a.no_fast_posterior = h->kernel_variant == 6;
         const void *k = chain_kernel_ptr(run.fwd, (R + kChainWarps - 1) / kChainWarps);
         const uint32_t smem = chain_smem_bytes(R, run.max_classes, run.fwd);
-        if (!h->chain_attr_done) {
+        if (first_time_on_device(h->device, 2)) {
             for (uint32_t n = 1; n <= (uint32_t)kChainMaxNIT; ++n)
                 for (bool f : {false, true})
                     GG_CUDA(cudaFuncSetAttribute(chain_kernel_ptr(f, n), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
-            h->chain_attr_done = true;
         }
         void *params[] = {(void *)&a};
         GG_CUDA(cudaLaunchKernel(k, dim3(1), dim3(kChainThreads), params, smem, h->stream));
         ++h->stats.n_launches;
     }
 
-    static void set_attrs() {
-        static bool done = false;   // per process and per T
-        if (done) return;
+    static void set_attrs(int device) {
+        if (!first_time_on_device(device, sizeof(T) == 4 ? 3 : 4)) return;
         for (int V : {1, 2, 4})
             for (int NS : {1, 2, 4, 8})
                 for (bool fwd : {false, true}) {
@@ -573,7 +578,6 @@ struct Engine {
                     const void *k = pick_kernel<T>(V, NS, fwd);
                     GG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
                 }
-        done = true;
     }
 
     // ---- host half of gg_hmm_create: sizes, checkpoint schedule, run fusion.  No CUDA call: a worker thread can do it
@@ -623,7 +627,7 @@ struct Engine {
     static void create_device(gg_hmm *h) {
         Plan &pl = h->plan;
         const uint32_t C = pl.n_columns;
-        set_attrs();
+        set_attrs(h->device);
         h->d_cols.upload(h->host_cols, h->stream);
         h->d_em_side.upload(pl.em_side, h->stream);
         h->d_em_prob.upload(pl.em_prob, h->stream);
