@@ -48,7 +48,8 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
+         "clocks.mem,temperature.gpu")
 
     def __init__(self, index):
         self.index = index
@@ -76,7 +77,7 @@ class ClockSampler:
             self.proc.wait(2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
+        sm, mx, reasons, power, mem, temp = [], [], set(), [], [], []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -85,11 +86,16 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
             except ValueError:
                 continue
+            try:
+                mem.append(float(f[9])); temp.append(float(f[10]))
+            except (ValueError, IndexError):
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "mem_mhz": float(np.median(mem)) if mem else None,
+                "temp_c_max": max(temp) if temp else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -261,21 +267,25 @@ def main():
 
     # ---- end to end through the C ABI with host buffers: plan + H2D + sweep + D2H (+ gather for N > 1)
     e2e_steps = max(1, args.steps)
+    def gather_posteriors(values):
+        if dist is None:
+            return
+        import torch
+        buf = torch.from_numpy(values).cuda()
+        out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, out, dst=0)
+        torch.cuda.synchronize()
+
     for _ in range(2):
-        capi.hmm_run(cp, device=local_rank)      # warm (the state arena of the previous call is reused)
+        gather_posteriors(capi.hmm_run(cp, device=local_rank).values)   # warm (arena reuse, NCCL gather channel)
     barrier()
     e2e_step_ms = []
     t1 = time.perf_counter()
     for _ in range(e2e_steps):
         ts = time.perf_counter()
         r = capi.hmm_run(cp, device=local_rank)
+        gather_posteriors(r.values)
         e2e_step_ms.append(1e3 * (time.perf_counter() - ts))
-        if dist is not None:
-            import torch
-            buf = torch.from_numpy(r.values).cuda()
-            out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-            dist.gather(buf, out, dst=0)
-            torch.cuda.synchronize()
     barrier()
     e2e_wall = time.perf_counter() - t1
     assert np.array_equal(r.values, res_dev), "e2e and resident runs disagree"
@@ -286,6 +296,11 @@ def main():
     # ---- max over ranks
     if dist is not None:
         import torch
+        mine = torch.tensor([my_ms / args.steps, float(clocks.get("sm_mhz") or 0), float(clocks.get("power_w_max") or 0),
+                             float(clocks.get("temp_c_max") or 0)], dtype=torch.float64, device="cuda")
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(x), 1) for x in r.tolist()] for r in allr]
         t = torch.tensor([my_ms, wall * 1e3, e2e_wall * 1e3], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         my_ms, wall_ms, e2e_ms = [float(x) for x in t.tolist()]
@@ -294,6 +309,7 @@ def main():
         total_cols, total_states = [float(x) for x in tot.tolist()]
     else:
         wall_ms, e2e_ms = wall * 1e3, e2e_wall * 1e3
+        per_rank = None
         total_cols, total_states = float(problem.n_columns), float(st0["state_columns"])
     if rank != 0:
         dist.destroy_process_group()
@@ -346,6 +362,7 @@ def main():
                 (" + gather of posteriors to rank 0" if world > 1 else "")},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,
+        "per_rank": ({"columns": ["device_ms_per_step", "sm_mhz", "power_w_max", "temp_c_max"], "rows": per_rank} if per_rank else None),
         "checkpoint_levels": st0["checkpoint_levels"], "state_bytes_reserved": st0["state_bytes_reserved"],
         "max_untagged": st0["max_untagged"],
     }

@@ -48,21 +48,21 @@ struct CudaError : std::runtime_error {
         }                                                                                                     \
     } while (0)
 
+// A typed view into the handle's table arena (one allocation per handle, cached across handles: a dozen
+// cudaMalloc/cudaFree pairs per call cost more than the sweep of a small chromosome).
 template <typename U>
 struct DevBuf {
     U *p = nullptr;
     size_t n = 0;
-    void alloc(size_t count) {
-        release();
+    void bind(void *base, size_t count) {
+        p = count ? static_cast<U *>(base) : nullptr;
         n = count;
-        if (count) GG_CUDA(cudaMalloc(&p, count * sizeof(U)));
     }
     void upload(const std::vector<U> &h, cudaStream_t st) {
-        alloc(h.size());
+        if (h.size() != n) throw std::runtime_error("internal: table size mismatch");
         if (!h.empty()) GG_CUDA(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(U), cudaMemcpyHostToDevice, st));
     }
     void release() {
-        if (p) cudaFree(p);
         p = nullptr;
         n = 0;
     }
@@ -77,6 +77,7 @@ struct DevBuf {
 struct ArenaCache {
     std::mutex mu;
     std::map<int, std::pair<unsigned char *, size_t>> slot;
+    // two slots per device: key = 2*device (state arena) or 2*device+1 (table arena)
     unsigned char *take(int dev, size_t need, size_t &got) {
         std::lock_guard<std::mutex> g(mu);
         auto it = slot.find(dev);
@@ -146,8 +147,10 @@ struct gg_hmm {
     DevBuf<double> d_em_prob, d_scale_a, d_scale_b, d_result;
     DevBuf<uint16_t> d_row_order;
     DevBuf<unsigned char> d_partial;
-    unsigned char *arena = nullptr;
+    unsigned char *arena = nullptr;      // state arena (columns, F/G tables)
     size_t arena_bytes = 0;
+    unsigned char *tables = nullptr;     // table arena (everything else on the device)
+    size_t tables_bytes = 0;
     DevBuf<unsigned int> d_counter;
     // runs of consecutive single-block columns fused into one chain-kernel launch each
     struct Run { bool fwd; uint32_t first, n, max_classes; uint64_t in_off; int64_t in_col; };
@@ -164,7 +167,8 @@ struct gg_hmm {
     ~gg_hmm() {
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
-        if (arena) g_arena_cache.give(device, arena, arena_bytes);
+        if (arena) g_arena_cache.give(2 * device, arena, arena_bytes);
+        if (tables) g_arena_cache.give(2 * device + 1, tables, tables_bytes);
     }
 };
 
@@ -628,20 +632,47 @@ struct Engine {
         Plan &pl = h->plan;
         const uint32_t C = pl.n_columns;
         set_attrs(h->device);
+        h->max_grid = (uint32_t)h->num_sms * 16;
+        // one table arena: sub-allocations at 256-byte granularity
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t o_cols = carve(h->host_cols.size() * sizeof(ColDesc));
+        const size_t o_side = carve(pl.em_side.size());
+        const size_t o_prob = carve(pl.em_prob.size() * sizeof(double));
+        const size_t o_al = carve(pl.allele1.size());
+        const size_t o_ro = carve(pl.row_order.size() * sizeof(uint16_t));
+        const size_t o_ch = carve(h->chain_steps.size() * sizeof(ChainStep));
+        const size_t o_sa = carve((size_t)C * sizeof(double));
+        const size_t o_sb = carve((size_t)C * sizeof(double));
+        const size_t o_res = carve((size_t)pl.gl_offsets[C] * sizeof(double));
+        const size_t o_cnt = carve(sizeof(unsigned int));
+        const size_t o_part = carve((size_t)h->max_grid * kPartialStride * sizeof(T));
+        const size_t need = off + 256;
+        h->tables = g_arena_cache.take(2 * h->device + 1, need, h->tables_bytes);
+        if (!h->tables) {
+            GG_CUDA(cudaMalloc(&h->tables, need));
+            h->tables_bytes = need;
+        }
+        unsigned char *tb = h->tables;
+        h->d_cols.bind(tb + o_cols, h->host_cols.size());
+        h->d_em_side.bind(tb + o_side, pl.em_side.size());
+        h->d_em_prob.bind(tb + o_prob, pl.em_prob.size());
+        h->d_allele1.bind(tb + o_al, pl.allele1.size());
+        h->d_row_order.bind(tb + o_ro, pl.row_order.size());
+        h->d_chain_steps.bind(tb + o_ch, h->chain_steps.size());
+        h->d_scale_a.bind(tb + o_sa, C);
+        h->d_scale_b.bind(tb + o_sb, C);
+        h->d_result.bind(tb + o_res, pl.gl_offsets[C]);
+        h->d_counter.bind(tb + o_cnt, 1);
+        h->d_partial.bind(tb + o_part, (size_t)h->max_grid * kPartialStride * sizeof(T));
         h->d_cols.upload(h->host_cols, h->stream);
         h->d_em_side.upload(pl.em_side, h->stream);
         h->d_em_prob.upload(pl.em_prob, h->stream);
         h->d_allele1.upload(pl.allele1, h->stream);
         h->d_row_order.upload(pl.row_order, h->stream);
-        if (!h->chain_steps.empty()) h->d_chain_steps.upload(h->chain_steps, h->stream);
-        h->d_scale_a.alloc(C);
-        h->d_scale_b.alloc(C);
-        h->d_result.alloc(pl.gl_offsets[C]);
-        h->d_counter.alloc(1);
+        h->d_chain_steps.upload(h->chain_steps, h->stream);
         GG_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned int), h->stream));
-        h->max_grid = (uint32_t)h->num_sms * 16;
-        h->d_partial.alloc((size_t)h->max_grid * kPartialStride * sizeof(T));
-        h->arena = g_arena_cache.take(h->device, h->sched.arena_bytes, h->arena_bytes);
+        h->arena = g_arena_cache.take(2 * h->device, h->sched.arena_bytes, h->arena_bytes);
         if (!h->arena && h->sched.arena_bytes) {
             GG_CUDA(cudaMalloc(&h->arena, h->sched.arena_bytes));
             h->arena_bytes = h->sched.arena_bytes;
@@ -766,7 +797,7 @@ static uint64_t default_budget(const gg_options *o, int device) {
     if (budget == 0) {
         size_t free_b = 0, total_b = 0;
         GG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        const uint64_t cached = g_arena_cache.cached(device);
+        const uint64_t cached = g_arena_cache.cached(2 * device);
         budget = (uint64_t)((free_b + cached) * 0.9);
         // free memory jitters by a few MB between calls; plan for the retired arena when it is about the size the
         // budget asks for, so that it is reused instead of being freed and allocated again (hundreds of ms at >100 GB)
@@ -970,12 +1001,23 @@ int gg_hmm_debug_scales(gg_hmm *h, double *alpha_scale, double *beta_scale) {
 int gg_hmm_run(const gg_problem *p, const gg_options *o, gg_result **out, char *err, size_t errlen) {
     if (out) *out = nullptr;
     gg_hmm *h = nullptr;
+    const bool trace = std::getenv("GG_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms_since = [&] { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     int rc = gg_hmm_create(p, o, &h, err, errlen);
     if (rc != GG_OK) return rc;
+    const float t_create = ms_since();
     rc = gg_hmm_sweep(h, 0, err, errlen);
+    const float t_sweep = ms_since();
     if (rc == GG_OK) rc = gg_hmm_fetch(h, out, err, errlen);
+    const float t_fetch = ms_since();
     const bool was_fp32 = !h->fp64;
+    const float dev_ms = h->stats.last_sweep_ms;
+    const unsigned long long arena_b = h->arena_bytes;
     gg_hmm_destroy(h);
+    if (trace)
+        std::fprintf(stderr, "[gg run] create %.1f ms, sweep %.1f (device %.1f), fetch %.1f, destroy %.1f, arena %llu B\n", t_create,
+                     t_sweep - t_create, dev_ms, t_fetch - t_sweep, ms_since() - t_fetch, arena_b);
     if (rc != GG_OK || !was_fp32) return rc;
     // Range guard of the fp32 path: per-column scaling keeps well-conditioned chains far from underflow, but reads
     // that contradict each other at 1e-10 per site over many sites can push every state of a column below fp32's
