@@ -917,6 +917,34 @@ void gg_hmm_destroy(gg_hmm *h) {
 
 void gg_arena_release(void) { g_arena_cache.clear(); }
 
+// STREAM-style device copy bandwidth (read + write bytes per second, best of `reps`), the same measurement that
+// defines the roofline denominator; lets a benchmark report what THIS device does on the day.
+double gg_device_copy_gbs(int device, uint64_t bytes, int reps) {
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return 0.0;
+    unsigned char *a = nullptr, *b = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    double best = 0.0;
+    if (cudaMalloc(&a, bytes) == cudaSuccess && cudaMalloc(&b, bytes) == cudaSuccess && cudaEventCreate(&e0) == cudaSuccess &&
+        cudaEventCreate(&e1) == cudaSuccess) {
+        cudaMemset(a, 1, bytes);
+        for (int i = 0; i < reps + 1; ++i) {
+            cudaEventRecord(e0);
+            cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice);
+            cudaEventRecord(e1);
+            if (cudaEventSynchronize(e1) != cudaSuccess) break;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (i > 0 && ms > 0.f) best = std::max(best, 2.0 * (double)bytes / (ms * 1e6));
+        }
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (a) cudaFree(a);
+    if (b) cudaFree(b);
+    cudaGetLastError();
+    return best;
+}
+
 // Independent chains back to back on one device; chain i+1 is planned and scheduled on a host thread while the device
 // sweeps chain i (the reference plans and sweeps one chromosome after the other, giggles/cli/genotype.py:196-338).
 int gg_hmm_run_batch(const gg_problem *problems, uint32_t n, const gg_options *o, gg_result **results, char *err, size_t errlen) {

@@ -498,7 +498,8 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                         float dot = 0.f;
 #pragma unroll
                         for (int v = 0; v < V; ++v) {
-                            o[v] = fmaf(kx[s][v], fk * x[v], fmaf(kx1[s][v], x1[v], rowterm + kc[s][v]));
+                            const float rest = two ? fmaf(kx1[s][v], x1[v], rowterm + kc[s][v]) : rowterm + kc[s][v];
+                            o[v] = fmaf(kx[s][v], fk * x[v], rest);
                             dot = fmaf(o[v], gout[s][v], dot);
                             colacc[s][v] = fmaf(fo, o[v], colacc[s][v]);      // times gout once per block, below
                         }

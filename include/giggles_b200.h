@@ -194,6 +194,9 @@ int gg_schedule_dry_run(uint32_t n_columns, const uint64_t *col_bytes, const uin
                         uint64_t *arena_bytes, uint32_t *levels, uint64_t *n_bwd, uint64_t *n_fwd,
                         char *err, size_t errlen);
 
+/* diagnostic: device-to-device copy bandwidth in GB/s (read + write), best of `reps` copies of `bytes` */
+double gg_device_copy_gbs(int device, uint64_t bytes, int reps);
+
 const char *gg_version(void);
 int gg_device_count(void);
 
