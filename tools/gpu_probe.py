@@ -40,6 +40,9 @@ if "r400" in which:
 if "r94" in which:
     run("R=94 mc=15 C=48", config2_window(48, max_coverage=15, n_haps=94))
     run("R=94 mc=15 C=48 generic", config2_window(48, max_coverage=15, n_haps=94), kv=1)
+if "cw16" in which:
+    run("cfg2 mc=15 C=160 auto", config2_window(160, max_coverage=15), reps=2)
+    run("cfg2 mc=15 C=160 one CTA x 16 warps", config2_window(160, max_coverage=15), reps=2, kv=2)
 if "big" in which:
     run("cfg2 mc=15 C=48", config2_window(48, max_coverage=15))
     run("cfg2 mc=15 C=160 (checkpointed)", config2_window(160, max_coverage=15), reps=1)
