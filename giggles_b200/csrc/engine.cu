@@ -225,7 +225,7 @@ static const void *pick_kernel(int V, int NS, bool fwd) {
 
 static constexpr size_t kMaxDynSmem = 200 * 1024;
 static constexpr size_t kMaxDynSmemTma = 222 * 1024;   // 227 KB per CTA minus the kernel's static shared memory
-static constexpr size_t kMaxDynSmemTma2 = 111 * 1024;  // two CTAs per SM: (228 KB - 2 * (1 KB reserved + static)) / 2
+static constexpr size_t kMaxDynSmemTma2 = 112 * 1024;  // two CTAs per SM: (228 KB - 2 * (1 KB reserved + <1 KB static)) / 2
 
 template <typename T>
 struct Engine {

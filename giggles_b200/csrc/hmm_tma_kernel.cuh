@@ -15,6 +15,8 @@
 // With 3-8 stages of 30-40 KB an SM keeps >100 KB of loads in flight, which is what hides HBM latency; the
 // register-staged generic kernel cannot.
 #pragma once
+#include <type_traits>
+
 #include "hmm_kernels.cuh"
 
 namespace gg {
@@ -118,9 +120,8 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_full[kTmaMaxStages];
     __shared__ __align__(8) uint64_t s_empty[kTmaMaxStages];
-    __shared__ double s_W[kPartialStride];
-    __shared__ double s_L[GG_MAX_ALLELES * (GG_MAX_ALLELES + 1) / 2];
     __shared__ bool s_last;
+    __shared__ uint16_t s_seg[kTmaMaxConsumerWarps * 2 * kMaxClasses];   // forward, single tile: per row group, end of each class segment
 
     const uint32_t R = a.R, BS = a.BS;
     const uint32_t RR = R * R;
@@ -172,6 +173,16 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
         for (uint32_t t = tid; t < R; t += blockDim.x) {
             const uint32_t R1 = (FWD && a.row_order) ? a.row_order[t] : t;
             s_rowmeta[t] = pack_row(R1, 0, R, s_al_o[R1], s_al_i[R1]);
+        }
+        if (FWD && G == 32) {
+            // rows are class-sorted and dealt round-robin to the row groups: group g owns sorted rows g, g+ngrp, ...;
+            // its rows of class <= c are the first ceil((B_c - g) / ngrp) of them, B_c = #rows of class <= c
+            for (uint32_t q = tid; q < ngrp * NCo; q += blockDim.x) {
+                const uint32_t g = q / NCo, c = q % NCo;
+                uint32_t B = 0;
+                for (uint32_t r = 0; r < R; ++r) B += s_al_o[r] <= c ? 1u : 0u;
+                s_seg[g * kMaxClasses + c] = (uint16_t)(B > g ? (B - g + ngrp - 1) / ngrp : 0u);
+            }
         }
     } else if (tid < n_tiles) {
         const uint32_t row0 = tid * TR, row1 = min(R, row0 + TR);
@@ -294,6 +305,10 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
             a2i[s][v] = cok[s] ? s_al_i[ccol[s] + v] : 0u;
         }
     }
+    uint32_t cokm[NS];                                     // all-ones where the lane's slot holds real columns
+#pragma unroll
+    for (int s = 0; s < NS; ++s) cokm[s] = cok[s] ? 0xffffffffu : 0u;
+    const uint32_t gl0m = gl == 0 ? 0xffffffffu : 0u;
     float qc[NS][V];
 #pragma unroll
     for (int s = 0; s < NS; ++s)
@@ -451,12 +466,14 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
             }
             const uint2 *meta_t = s_rowmeta + t * L.TRp + grp;
 
-#pragma unroll (NS == 1 ? (CWT == 16 ? 3 : 4) : 2)
-            for (uint32_t it = 0; it < L.n_iter_t; ++it) {
+            // one row of the block: `seg_cls4` >= 0 means the caller iterates a segment of rows of one allele class
+            // (class * 4 given, F of that class in `seg_fo`), so neither is looked up nor checked per row
+            auto row_body = [&](auto seg_tag, const uint32_t it, const uint32_t seg_cls4, const float seg_fo) {
+                constexpr bool SEG = decltype(seg_tag)::value;      // compile-time: two separate loop bodies
                 const uint2 meta = meta_t[it * ngrp];
                 const uint32_t rowb = meta.x & 0x7fffffffu;
-                const uint32_t r1b = meta.y & 0xfffu, a1ob = (meta.y >> 12) & 0x7fu, a1ib = (meta.y >> 19) & 0x7fu;
-                const bool rvalid = (int32_t)meta.x < 0;
+                const uint32_t r1b = meta.y & 0xfffu, a1ib = (meta.y >> 19) & 0x7fu;
+                const uint32_t a1ob = SEG ? seg_cls4 : (meta.y >> 12) & 0x7fu;
                 float rowsum_in = *reinterpret_cast<const float *>(xrow + r1b);
                 float fk1 = 0.f;
                 if (two) {
@@ -464,9 +481,9 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                     if (!FWD) fk1 = *reinterpret_cast<const float *>(fgi1_b + a1ib);
                 }
                 const float rowterm = cB * rowsum_in;
-                const float fo = *reinterpret_cast<const float *>(fgo_b + a1ob);
+                const float fo = SEG ? seg_fo : *reinterpret_cast<const float *>(fgo_b + a1ob);
                 const float fk = weigh ? *reinterpret_cast<const float *>(fgi_b + a1ib) : 1.f;
-                if (FWD && a1ob != cur_cls) {         // row class changed: park the posterior accumulators
+                if (FWD && !SEG && a1ob != cur_cls) {   // row class changed: park the posterior accumulators
                     if (cur_cls != 0xffffffffu) park_q();
                     cur_cls = a1ob;
                 }
@@ -491,9 +508,9 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
 #pragma unroll
                         for (int v = 0; v < V; ++v) {
                             o[v] = fo * fmaf(kx[s][v], x[v], fmaf(kr[s][v], rowterm, kc[s][v]));
-                            rs += o[v];
                             colacc[s][v] += o[v];
                         }
+                        rs += V == 4 ? (o[0] + o[1]) + (o[V > 2 ? 2 : 0] + o[V > 3 ? 3 : 0]) : o[0] + o[1];
                     } else {
                         float dot = 0.f;
 #pragma unroll
@@ -505,7 +522,8 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                         }
                         rs = fmaf(fo, dot, rs);
                     }
-                    if (rvalid && cok[s]) st_vec<V>(ocolp[s] + rowb, o);
+                    // valid row (sign bit of the metadata word) AND a live column slot, in one test
+                    if ((int32_t)(meta.x & cokm[s]) < 0) st_vec<V>(ocolp[s] + rowb, o);
                     if (FWD) {
                         float bv[V];
                         lds_vec<V>(bv, bcolp[s] + rowb);
@@ -515,8 +533,27 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                 }
 #pragma unroll
                 for (int sh = G >> 1; sh > 0; sh >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, sh);
-                if (gl == 0 && rvalid) *reinterpret_cast<float *>(reinterpret_cast<char *>(rsum) + r1b) = rs;
+                if ((int32_t)(meta.x & gl0m) < 0) *reinterpret_cast<float *>(reinterpret_cast<char *>(rsum) + r1b) = rs;
                 totacc += rs;        // identical in every lane of the row group; padding rows contribute 0
+            };
+
+            if (FWD && !MT && G == 32) {
+                // single tile, one row group per warp: rows are class-sorted, so walk them class by class
+                uint32_t it = 0;
+                for (uint32_t cls = 0; cls < NCo; ++cls) {
+                    const uint32_t end = s_seg[grp * kMaxClasses + cls];
+                    if (it < end) {
+                        const float seg_fo = fgo[cls];
+#pragma unroll 4
+                        for (; it < end; ++it) row_body(std::true_type{}, it, cls * 4, seg_fo);
+                        cur_cls = cls * 4;
+                        park_q();
+                    }
+                }
+                cur_cls = 0xffffffffu;
+            } else {
+#pragma unroll (NS == 1 ? (CWT == 16 ? 3 : 4) : 2)
+                for (uint32_t it = 0; it < L.n_iter_t; ++it) row_body(std::false_type{}, it, 0u, 0.f);
             }
             // ---- hand the stages back
             __syncwarp();
@@ -590,6 +627,9 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
     consumer_bar(nct);
     if (!s_last) return;
     __threadfence();
+    // the last CTA's final reduction borrows the (now idle) first stage for its fp64 scratch
+    double *s_W = reinterpret_cast<double *>(smem_raw + L.off_stage);
+    double *s_L = s_W + kPartialStride;
     const uint32_t npair = FWD ? NCo * NCo : 0u;
     for (uint32_t p = ctid; p < npair + 1; p += nct) {
         const uint32_t slot = (p == npair) ? (uint32_t)(kMaxClasses * kMaxClasses) : p;
