@@ -134,7 +134,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config2", "config1", "tagged", "config5"],
+    ap.add_argument("--workload", default="config2", choices=["config2", "config1", "tagged", "config4", "config5"],
                     help="config2 (default, the headline): chr20-scale window; the others are side measurements of the "
                          "remaining BASELINE.json shapes")
     ap.add_argument("--columns", type=int, default=None, help="variant sites per window (one step sweeps one window)")
@@ -146,7 +146,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    presets = {"config2": (256, 15, 88), "config1": (5000, 15, 10), "tagged": (20000, 15, 88), "config5": (48, 8, 400)}
+    presets = {"config2": (256, 15, 88), "config1": (5000, 15, 10), "tagged": (20000, 15, 88), "config4": (8, 20, 88),
+               "config5": (48, 8, 400)}
     d_cols, d_cov, d_haps = presets[args.workload]
     if args.columns is None:
         args.columns = d_cols
@@ -167,6 +168,8 @@ def main():
             return synth.config2_window(n_columns, seed=seed, tags="all", n_haps=n_haps)
         if args.workload == "config5":
             return synth.config5_window(n_columns, seed=seed, n_haps=n_haps, max_coverage=max_coverage)
+        if args.workload == "config4":
+            return synth.config4_window(n_columns, seed=seed, n_haps=n_haps, max_coverage=max_coverage)
         return synth.config2_window(n_columns, seed=seed, max_coverage=max_coverage, n_haps=n_haps)
 
     names = {"config2": f"configs[1] chr20-scale window: {args.columns} of 516k variant sites, {args.haps}-haplotype panel, "
@@ -174,6 +177,8 @@ def main():
              "config1": f"configs[0] 1 Mb region: {args.columns} variant sites, 10-haplotype panel, 10x HiFi untagged",
              "tagged": f"configs[1] shape with every read haplotagged (the mode giggles runs in without --keep-untagged): "
                        f"{args.columns} variant sites, {args.haps}-haplotype panel, one {args.haps}^2 block per column",
+             "config4": f"configs[3] shape: {args.columns} variant sites of 60x ONT, {args.haps}-haplotype panel, max-coverage "
+                        f"{args.max_coverage} (2^{args.max_coverage} bipartition blocks = {(1 << args.max_coverage) * args.haps ** 2 * 4 / 2**30:.1f} GiB per column)",
              "config5": f"configs[4] shape: {args.columns} variant sites, {args.haps}-haplotype panel, 3..16 alleles per site, "
                         f"max-coverage {args.max_coverage}"}
     config = {"workload": names[args.workload],

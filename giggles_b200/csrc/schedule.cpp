@@ -123,6 +123,27 @@ struct Builder {
             // too tight for one extra level: spend about half of what is left on checkpoints and recurse into the
             // parts, always leaving them room for two rolling columns plus two more (a part can then split again)
             const uint64_t M = avail > 2 * maxfg ? (avail - 2 * maxfg) / std::max<uint64_t>(maxcol, 1) : 0;
+            if (M < 5 && avail >= roll) {
+                // Room for two rolling columns only (columns of tens of GB): recompute the backward chain from the
+                // range's last column for every forward column.  Quadratic in the range length, which is a handful
+                // of columns when a single column takes a fifth of HBM.
+                const uint64_t mark = top;
+                uint64_t rbuf[2], fbuf[2];
+                rbuf[0] = alloc(maxcol); rbuf[1] = alloc(maxcol);
+                fbuf[0] = alloc(maxfg); fbuf[1] = alloc(maxfg);
+                for (uint32_t c = lo; c <= hi; ++c) {
+                    uint64_t cur = beta_hi;
+                    emit(hi, hi, fbuf[hi & 1]);
+                    for (uint32_t x = hi; x > c; --x) {
+                        emit(x - 1, x - 1, fbuf[(x - 1) & 1]);
+                        bwd(x - 1, cur, rbuf[(x - 1) & 1], fbuf[x & 1], fbuf[(x - 1) & 1]);
+                        cur = rbuf[(x - 1) & 1];
+                    }
+                    fwd(c, cur, fbuf[c & 1]);
+                }
+                top = mark;
+                return;
+            }
             if (M < 5)
                 throw std::runtime_error("state budget too small for this problem: " + std::to_string(avail) +
                                          " bytes left for a range whose largest column takes " + std::to_string(maxcol));

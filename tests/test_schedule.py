@@ -45,3 +45,12 @@ def test_budget_too_small_is_an_error():
 def test_single_and_empty():
     assert capi.schedule_dry_run([1000], [100], 1 << 20)["n_fwd"] == 1
     assert capi.schedule_dry_run([], [], 1 << 20)["n_fwd"] == 0
+
+
+def test_columns_of_a_fifth_of_hbm_use_the_quadratic_fallback():
+    # configs[3] with R = 88: one column is 33 GB; only two rolling backward columns fit beside alpha and the last beta
+    col, fg = 33_235_664_896, 50_331_648
+    r = capi.schedule_dry_run([col] * 8, [fg] * 8, 171_000_000_000)
+    assert r["n_fwd"] == 8 and r["n_bwd"] == 1 + 8 * 7 // 2 and r["arena_bytes"] <= 171_000_000_000
+    with pytest.raises(capi.GGError):
+        capi.schedule_dry_run([col] * 8, [fg] * 8, 140_000_000_000)
