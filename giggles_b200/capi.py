@@ -55,6 +55,16 @@ class gg_options(C.Structure):
     ]
 
 
+class gg_readset_view(C.Structure):
+    _fields_ = [
+        ("n_reads", C.c_uint32),
+        ("read_variant_offset", C.POINTER(C.c_uint64)),
+        ("variant_position", C.POINTER(C.c_int32)),
+        ("variant_quality", C.POINTER(C.c_int32)),
+        ("read_source_id", C.POINTER(C.c_int32)),
+    ]
+
+
 class gg_stats(C.Structure):
     _fields_ = [
         ("n_columns", C.c_uint64),
@@ -89,6 +99,7 @@ SYMBOLS = [
     "gg_plan_compatible_prev", "gg_plan_free",
     "gg_entry_emission", "gg_entry_emission_batch", "gg_transition_scalars", "gg_binomial_coefficient",
     "gg_schedule_dry_run", "gg_version", "gg_device_count", "gg_device_copy_gbs",
+    "gg_readselection", "gg_pyset_replay",
 ]
 
 _lib = None
@@ -138,6 +149,10 @@ def lib() -> C.CDLL:
     L.gg_plan_compatible_prev.restype = u32
     L.gg_plan_free.argtypes = [vp]
     L.gg_plan_free.restype = None
+    L.gg_readselection.argtypes = [C.POINTER(gg_readset_view), u32, C.POINTER(i32), u32, C.c_int, C.POINTER(u32),
+                                   C.POINTER(u32)] + errargs
+    L.gg_pyset_replay.argtypes = [C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64), C.c_int64]
+    L.gg_pyset_replay.restype = C.c_int64
     L.gg_entry_emission.argtypes = [C.POINTER(dbl), u32, i32, dbl, C.POINTER(dbl)]
     L.gg_entry_emission.restype = None
     L.gg_entry_emission_batch.argtypes = [C.POINTER(dbl), C.POINTER(u64), u64, i32, dbl, C.POINTER(dbl)]
@@ -341,6 +356,41 @@ class PlanView:
         if getattr(self, "_h", None):
             lib().gg_plan_free(self._h)
             self._h = None
+
+
+def readselection_flat(read_variant_offset, variant_position, variant_quality, read_source_id, max_cov: int,
+                       preferred_source_ids=None, bridging: bool = True) -> np.ndarray:
+    """``gg_readselection`` on flat arrays; returns the selected read indices, increasing."""
+    off = np.ascontiguousarray(read_variant_offset, dtype=np.uint64)
+    pos = np.ascontiguousarray(variant_position, dtype=np.int32)
+    qual = np.ascontiguousarray(variant_quality, dtype=np.int32)
+    src = np.ascontiguousarray(read_source_id, dtype=np.int32)
+    n = off.size - 1
+    if n < 0 or src.size != n or pos.size != qual.size or (n >= 0 and int(off[-1]) != pos.size):
+        raise ValueError("readselection_flat: inconsistent array sizes")
+    view = gg_readset_view(n, as_ptr(off, C.c_uint64), as_ptr(pos, C.c_int32), as_ptr(qual, C.c_int32),
+                           as_ptr(src, C.c_int32))
+    pref = None if preferred_source_ids is None else np.ascontiguousarray(sorted(preferred_source_ids), dtype=np.int32)
+    out = np.empty(max(n, 1), dtype=np.uint32)
+    cnt = C.c_uint32()
+    err = C.create_string_buffer(512)
+    rc = lib().gg_readselection(C.byref(view), int(max_cov), None if pref is None else as_ptr(pref, C.c_int32),
+                                0 if pref is None else pref.size, int(bool(bridging)), as_ptr(out, C.c_uint32),
+                                C.byref(cnt), err, len(err))
+    if rc == 2:
+        raise ValueError(err.value.decode())
+    _check(rc, err)
+    return out[:cnt.value].copy()
+
+
+def pyset_replay(ops, cap: int) -> list:
+    """Test hook: iteration orders of the order-exact Python-set model after a script of operations."""
+    a = np.ascontiguousarray(ops, dtype=np.int64)
+    out = np.empty(cap, dtype=np.int64)
+    n = lib().gg_pyset_replay(as_ptr(a, C.c_int64), a.size, as_ptr(out, C.c_int64), cap)
+    if n < 0:
+        raise GGError(1, f"gg_pyset_replay: {n}")
+    return out[:n].tolist()
 
 
 def schedule_dry_run(col_bytes, fg_bytes, budget):

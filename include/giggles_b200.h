@@ -187,6 +187,27 @@ int32_t gg_binomial_coefficient(int32_t n, int32_t k);
 int gg_result_call(const gg_result *r, double gt_qual_threshold, int32_t *gt_index,
                    int32_t *gq, double *gl_log10);
 
+/* ---- read selection: readselection(readset, max_cov, preferred_source_ids, bridging)
+ *      of giggles/readselect.pyx:231-271 (called by giggles/utils.py:71-76 before every GenotypeHMM).
+ *      Host only.  The view is the flat image of what that code reads through cpp.ReadSet / cpp.Read
+ *      (getVariantCount, getPosition, getQuality, getSourceID — readselect.pyx:41-46,63-72,127-140).
+ *      Returns the selected read indices in increasing order (the reference returns a Python set that
+ *      ReadSet.subset turns into an ordered IndexSet, giggles/core.pyx:298-308).  Ties between equally
+ *      scored reads are resolved exactly as the reference resolves them under CPython 3.12 + libstdc++
+ *      (see giggles_b200/csrc/pyset.hpp).  rc 2 = a read covers fewer than two variants (ValueError there). */
+typedef struct gg_readset_view {
+    uint32_t n_reads;
+    const uint64_t *read_variant_offset; /* [n_reads+1] CSR into the two arrays below */
+    const int32_t *variant_position;     /* strictly increasing inside a read */
+    const int32_t *variant_quality;
+    const int32_t *read_source_id;       /* [n_reads] */
+} gg_readset_view;
+int gg_readselection(const gg_readset_view *rs, uint32_t max_cov, const int32_t *preferred_source_ids,
+                     uint32_t n_preferred, int bridging, uint32_t *selected, uint32_t *n_selected, char *err,
+                     size_t errlen);
+/* test hook: replays a script of Python-set operations on the order-exact set model (readselect.cpp) */
+int64_t gg_pyset_replay(const int64_t *ops, int64_t n, int64_t *out, int64_t cap);
+
 /* ---- checkpoint schedule dry run (host only, no device): builds and self-checks the launch
  *      schedule gg_hmm_create would use for columns of the given byte sizes under `budget`.
  *      The reference's fixed sqrt(C) schedule is src/genotypehmm.cpp:130,153-156,364-383. */

@@ -15,7 +15,8 @@ fi
 W="$(mktemp -d /tmp/giggles_dropin.XXXXXX)"
 trap 'rm -rf "$W"' EXIT
 cp -r "$REF/giggles" "$W/giggles"; cp -r "$REF/src" "$W/src"; chmod -R u+w "$W"
-cp "$HERE/genotypehmm.h" "$HERE/genotypehmm.cpp" "$W/src/"          # <- the whole change to the reference tree
+cp "$HERE/genotypehmm.h" "$HERE/genotypehmm.cpp" "$W/src/"          # <- the change to the reference tree: the HMM ...
+cp "$HERE/readselect.pyx" "$W/giggles/readselect.pyx"                # <- ... and read selection
 echo 'version = "0+b200"' > "$W/giggles/_version.py"
 CXXFLAGS="-std=c++11 -include cstdint -O2 -fPIC -UNDEBUG -w"
 PYINC=$(python3 -c "import sysconfig;print(sysconfig.get_paths()['include'])")

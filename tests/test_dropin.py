@@ -42,3 +42,40 @@ def test_dropin_matches_reference_golden():
         assert "error" not in r, r
         assert r["nan"] == 0
         assert r["max_rel_big"] <= 1e-5 and r["max_abs_small"] <= 2e-6, r
+
+
+_READSELECT = r"""
+import json, sys
+import numpy as np
+from giggles.core import Read, ReadSet, readselection
+d = np.load(sys.argv[1])
+cur = {k: 0 for k in ("off", "pos", "qual", "src", "pref", "sel")}
+bad = []
+for i in range(len(d["max_cov"])):
+    c = {}
+    for k in cur:
+        n = int(d[k + "_len"][i]); c[k] = d[k][cur[k]:cur[k] + n].tolist(); cur[k] += n
+    rs = ReadSet()
+    for k in range(len(c["src"])):
+        r = Read("r%d" % k, 60, c["src"][k], 0)
+        for e in range(c["off"][k], c["off"][k + 1]):
+            r.add_variant(c["pos"][e], 0, [0.0, -5.0], c["qual"][e])
+        rs.add(r)
+    pref = None if c["pref"] == [-1] else set(c["pref"])
+    sel = readselection(rs, int(d["max_cov"][i]), pref, bool(d["bridging"][i]))
+    if not isinstance(sel, set) or sorted(sel) != c["sel"]:
+        bad.append(i)
+print(json.dumps({"cases": int(len(d["max_cov"])), "bad": bad}))
+"""
+
+
+@needs_module
+def test_dropin_readselection_matches_reference_golden():
+    """giggles.core.readselection of the drop-in module (integration/readselect.pyx -> gg_readselection) through the
+    reference's own Read / ReadSet classes; host only, so this one also runs without a GPU."""
+    env = dict(os.environ, PYTHONPATH=BUILD)
+    out = subprocess.run([sys.executable, "-c", _READSELECT, os.path.join(ROOT, "tests", "golden", "readselect", "cases.npz")],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.splitlines()[-1])
+    assert res == {"cases": 160, "bad": []}
