@@ -127,6 +127,7 @@ struct Builder {
                 // Room for two rolling columns only (columns of tens of GB): recompute the backward chain from the
                 // range's last column for every forward column.  Quadratic in the range length, which is a handful
                 // of columns when a single column takes a fifth of HBM.
+                max_depth = std::max(max_depth, depth + 1);   // it recomputes: never report "everything fitted"
                 const uint64_t mark = top;
                 uint64_t rbuf[2], fbuf[2];
                 rbuf[0] = alloc(maxcol); rbuf[1] = alloc(maxcol);

@@ -52,5 +52,6 @@ def test_columns_of_a_fifth_of_hbm_use_the_quadratic_fallback():
     col, fg = 33_235_664_896, 50_331_648
     r = capi.schedule_dry_run([col] * 8, [fg] * 8, 171_000_000_000)
     assert r["n_fwd"] == 8 and r["n_bwd"] == 1 + 8 * 7 // 2 and r["arena_bytes"] <= 171_000_000_000
+    assert r["levels"] >= 2            # a recomputing schedule never reports "everything fitted"
     with pytest.raises(capi.GGError):
         capi.schedule_dry_run([col] * 8, [fg] * 8, 140_000_000_000)
