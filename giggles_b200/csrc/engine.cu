@@ -449,7 +449,12 @@ struct Engine {
         StepArgs<float> af;
         std::memcpy(&af, &a, sizeof(af));
         uint32_t ns = pick.stages, tr = pick.tr;
-        void *params[] = {(void *)&af, (void *)&ns, (void *)&tr};
+        static const uint32_t l2_ahead_env = [] {
+            const char *e = std::getenv("GG_L2_AHEAD");
+            return e ? (uint32_t)std::atoi(e) : kTmaL2Ahead;
+        }();
+        uint32_t l2a = l2_ahead_env;
+        void *params[] = {(void *)&af, (void *)&ns, (void *)&tr, (void *)&l2a};
         GG_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(threads), params, pick.L.total, h->stream));
         ++h->stats.n_launches;
         return true;

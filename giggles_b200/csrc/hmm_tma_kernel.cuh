@@ -23,6 +23,7 @@ namespace gg {
 
 constexpr int kTmaMaxStages = 8;
 constexpr int kTmaMaxConsumerWarps = 8;
+constexpr uint32_t kTmaL2Ahead = 513;   // producer's L2 prefetch: one round ahead, beta blocks only (see the producer loop); 0 = off; GG_L2_AHEAD overrides
 
 struct TmaStageMeta {
     uint32_t b_out, b_self, pad0, pad1;
@@ -90,6 +91,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 __device__ __forceinline__ void consumer_bar(uint32_t nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
+// hint: start moving `bytes` (multiple of 16) at `src` from HBM into L2; no completion tracking
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 template <int V>
 __device__ __forceinline__ void lds_vec(float (&d)[V], const void *p) {
     if (V == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); d[0] = t.x; d[1] = t.y; d[V > 2 ? 2 : 0] = t.z; d[V > 3 ? 3 : 0] = t.w; }
@@ -116,7 +122,7 @@ __device__ __forceinline__ uint2 pack_row(uint32_t R1, uint32_t row0, uint32_t R
 // V: floats per vector access (4: R % 4 == 0; 2: R % 4 == 2, e.g. a 47-sample / 94-haplotype panel).
 template <bool FWD, int G, int NS, bool MT, int CWT, bool TWO, int V>
 __global__ void __launch_bounds__(32 * (1 + (CWT ? CWT : kTmaMaxConsumerWarps)), (CWT == 8 ? 2 : 1))
-step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t TR_arg) {
+step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t TR_arg, const uint32_t l2_ahead) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_full[kTmaMaxStages];
     __shared__ __align__(8) uint64_t s_empty[kTmaMaxStages];
@@ -229,6 +235,23 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
             const uint32_t b_out = nb_out, b_in0 = nb_in0;
             const float fo0 = pf_o0, fo1 = pf_o1, fi0 = pf_i0, fi1 = pf_i1;
             if (item + gridDim.x < n_items) prefetch(item + gridDim.x);
+            if (!MT && (l2_ahead & 255u)) {      // whole-block tiles only: a tiled block (up to 1 MB) would flood L2
+                // A forward item holds two stages (alpha, beta) of a three-stage ring, so the beta copy of the next
+                // item can only be issued when this item is done and its latency would be exposed.  Ask that block
+                // into L2 now: the copy is then served from L2.  l2_ahead = rounds of look-ahead | 512 (beta blocks
+                // only) | 1024 (input blocks only); lane j looks after load j of the far item.  Measured on the bench
+                // (DESIGN §7): beta only, one round: +3-5 % on the forward step; input blocks as well: no gain; two
+                // or more rounds: 5-25 % slower — the lines do not survive in L2 until they are used.
+                const uint64_t far = (uint64_t)item + (uint64_t)(l2_ahead & 255u) * gridDim.x;
+                const bool fb = FWD && lane == nred;
+                const bool want = (l2_ahead & 512u) ? fb : ((l2_ahead & 1024u) ? !fb : true);
+                if (far < n_items && lane < nload && want) {
+                    uint32_t bo, bi;
+                    decode((uint32_t)far, bo, bi);
+                    const uint32_t bk = fb ? bo : (FWD ? (bi | dev_pdep(lane, a.free_mask)) : (bi | (lane << a.n_sh)));
+                    bulk_prefetch_l2((fb ? a.beta : a.in) + (uint64_t)bk * BS, (fb ? RR : RR + 2u * R + 4u) * 4u);
+                }
+            }
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 const uint32_t row0 = t * TR, rows = min(TR, R - row0);
                 uint32_t subm = 0;
