@@ -23,7 +23,7 @@ namespace gg {
 
 constexpr int kTmaMaxStages = 8;
 constexpr int kTmaMaxConsumerWarps = 8;
-constexpr uint32_t kTmaL2Ahead = 513;   // producer's L2 prefetch: one round ahead, beta blocks only (see the producer loop); 0 = off; GG_L2_AHEAD overrides
+constexpr uint32_t kTmaL2Ahead = 2817;   // producer's L2 prefetch: one round ahead, beta blocks only, evict-last; beta copy evict-first (see the producer loop); 0 = off; GG_L2_AHEAD overrides
 
 struct TmaStageMeta {
     uint32_t b_out, b_self, pad0, pad1;
@@ -94,6 +94,25 @@ __device__ __forceinline__ void consumer_bar(uint32_t nthreads) { asm volatile("
 // hint: start moving `bytes` (multiple of 16) at `src` from HBM into L2; no completion tracking
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_prefetch_l2_hint(const void *src, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
 template <int V>
@@ -238,10 +257,13 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
             if (!MT && (l2_ahead & 255u)) {      // whole-block tiles only: a tiled block (up to 1 MB) would flood L2
                 // A forward item holds two stages (alpha, beta) of a three-stage ring, so the beta copy of the next
                 // item can only be issued when this item is done and its latency would be exposed.  Ask that block
-                // into L2 now: the copy is then served from L2.  l2_ahead = rounds of look-ahead | 512 (beta blocks
-                // only) | 1024 (input blocks only); lane j looks after load j of the far item.  Measured on the bench
-                // (DESIGN §7): beta only, one round: +3-5 % on the forward step; input blocks as well: no gain; two
-                // or more rounds: 5-25 % slower — the lines do not survive in L2 until they are used.
+                // into L2 now, marked evict-last so that it survives until the copy, and let the copy itself mark
+                // the lines evict-first (they are read once).  l2_ahead = rounds of look-ahead | 512 (beta blocks
+                // only) | 1024 (input blocks only) | 2048 (prefetch evict-last) | 256 (beta copy evict-first); lane j
+                // looks after load j of the far item.  Measured on the bench (same-box A/B): 513: +3-5 %
+                // on the forward step, 2561: +7 %, 2817 (the default): +8.5 %; input blocks as well: no gain;
+                // evict-first on the input copies: -2 %; two or more rounds ahead: 5-25 % slower even with
+                // evict-last — the lines do not survive in L2 until they are used.
                 const uint64_t far = (uint64_t)item + (uint64_t)(l2_ahead & 255u) * gridDim.x;
                 const bool fb = FWD && lane == nred;
                 const bool want = (l2_ahead & 512u) ? fb : ((l2_ahead & 1024u) ? !fb : true);
@@ -249,7 +271,10 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                     uint32_t bo, bi;
                     decode((uint32_t)far, bo, bi);
                     const uint32_t bk = fb ? bo : (FWD ? (bi | dev_pdep(lane, a.free_mask)) : (bi | (lane << a.n_sh)));
-                    bulk_prefetch_l2((fb ? a.beta : a.in) + (uint64_t)bk * BS, (fb ? RR : RR + 2u * R + 4u) * 4u);
+                    if (l2_ahead & 2048u)
+                        bulk_prefetch_l2_hint((fb ? a.beta : a.in) + (uint64_t)bk * BS, (fb ? RR : RR + 2u * R + 4u) * 4u, policy_evict_last());
+                    else
+                        bulk_prefetch_l2((fb ? a.beta : a.in) + (uint64_t)bk * BS, (fb ? RR : RR + 2u * R + 4u) * 4u);
                 }
             }
             for (uint32_t t = 0; t < n_tiles; ++t) {
@@ -272,6 +297,9 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
                         if (side && n_tiles == 1) {           // values and side record are contiguous: one copy
                             mbar_expect_tx(&s_full[s], row_bytes + side_bytes);
                             bulk_g2s(dst, blk, row_bytes + side_bytes, &s_full[s]);
+                        } else if (is_beta && n_tiles == 1 && (l2_ahead & 256u)) {
+                            mbar_expect_tx(&s_full[s], row_bytes);
+                            bulk_g2s_hint(dst, blk, row_bytes, &s_full[s], policy_evict_first());
                         } else {
                             mbar_expect_tx(&s_full[s], row_bytes + (side ? side_bytes : 0u));
                             bulk_g2s(dst, blk + (uint64_t)row0 * R, row_bytes, &s_full[s]);
