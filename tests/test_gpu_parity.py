@@ -301,3 +301,29 @@ def test_read_relabelling_symmetry_full_size():
     a = capi.hmm_run(p, device=0, precision=1).values
     b = capi.hmm_run(q, device=0, precision=1).values
     assert np.abs(a - b).max() < 1e-10
+
+
+_L2_KNOB = r"""
+import sys, hashlib
+sys.path.insert(0, sys.argv[1])
+from giggles_b200 import capi
+from giggles_b200.synth import config2_window
+p = config2_window(6, max_coverage=11)
+print(hashlib.sha256(capi.hmm_run(p, device=0).values.tobytes()).hexdigest())
+"""
+
+
+def test_l2_lookahead_is_a_pure_hint():
+    """The producer's L2 look-ahead (GG_L2_AHEAD, hmm_tma_kernel.cuh) only moves data towards L2: with it off, on,
+    or looking further ahead, the posteriors are bit-identical.  (Read once per process, hence subprocesses.)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = set()
+    for mode in ("0", "2817", "513", "3"):
+        out = subprocess.run([sys.executable, "-c", _L2_KNOB, root], env=dict(os.environ, GG_L2_AHEAD=mode),
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.add(out.stdout.strip().splitlines()[-1])
+    assert len(digests) == 1
