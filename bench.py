@@ -329,8 +329,16 @@ def main():
     # dominant kernel: the column-step kernel family; the forward step moves 12 B/state (read alpha_{c-1}, read
     # beta_c, write alpha_c), the backward step 8 B/state (read beta_c, write beta_{c-1})
     n_fwd, n_bwd = st0["n_forward_steps"], st0["n_backward_steps"]
-    fwd_gbs = 12.0 * S * args.steps / (fwd_ms / 1e3) / 1e9
-    bwd_gbs = 8.0 * S * (n_bwd / max(n_fwd, 1)) * args.steps / (bwd_ms / 1e3) / 1e9
+    # bytes per direction, exactly: a forward launch reads alpha_{c-1} and beta_c and writes alpha_c, a backward launch
+    # reads beta_{c+1} and writes beta_c; the engine's `scheduled_bytes` is that sum over every launch of the schedule
+    # (recompute launches of the checkpoint schedule included), so backward = scheduled - forward
+    u = problem.untagged_per_column().astype(np.int64)
+    rr = S / float(np.sum(2.0 ** u))                                  # R^2 of the device layout
+    sc = rr * 2.0 ** u
+    fwd_bytes = 4.0 * float(2.0 * sc.sum() + sc[:-1].sum())
+    bwd_bytes = float(st0["scheduled_bytes"]) - fwd_bytes
+    fwd_gbs = fwd_bytes * args.steps / (fwd_ms / 1e3) / 1e9
+    bwd_gbs = bwd_bytes * args.steps / (bwd_ms / 1e3) / 1e9
     dominant = "forward" if fwd_ms >= bwd_ms else "backward"
     ach = fwd_gbs if dominant == "forward" else bwd_gbs
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/, one launch of a
@@ -350,7 +358,7 @@ def main():
         "bound": "hbm", "kernel": f"step kernel, {dominant} (" + ("chain_kernel" if args.workload == "tagged" else "step_tma_kernel") + ")", "achieved": ach, "peak": peak, "unit": "GB/s",
         "frac": ach / peak, "box_copy_GBps": box_copy_gbs, "frac_of_box_copy": (ach / box_copy_gbs if box_copy_gbs else None),
         "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": (12.0 if dominant == "forward" else 8.0) * S / n_fwd,
+        "algorithmic_bytes_per_launch": (fwd_bytes / n_fwd) if dominant == "forward" else (bwd_bytes / n_bwd),
         "avg_launch_ms": (fwd_ms / (n_fwd * args.steps)) if dominant == "forward" else (bwd_ms / (n_bwd * args.steps)),
         "forward": {"GBps": fwd_gbs, "frac": fwd_gbs / peak, "launches_per_step": n_fwd, "ms_per_step": fwd_ms / args.steps},
         "backward": {"GBps": bwd_gbs, "frac": bwd_gbs / peak, "launches_per_step": n_bwd, "ms_per_step": bwd_ms / args.steps},

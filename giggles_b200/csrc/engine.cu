@@ -796,14 +796,15 @@ int gg_device_count(void) {
     return n;
 }
 
-// budget for the state arena: the caller's, or 90 % of what is free (the retired arena of the last handle counts as free)
+// budget for the state arena: the caller's, or 94 % of what is free (the retired arena of the last handle counts as free);
+// the rest (>= 10 GB on a B200) is left for the static tables, the result, the CUDA context and NCCL
 static uint64_t default_budget(const gg_options *o, int device) {
     uint64_t budget = o ? o->state_budget_bytes : 0;
     if (budget == 0) {
         size_t free_b = 0, total_b = 0;
         GG_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t cached = g_arena_cache.cached(2 * device);
-        budget = (uint64_t)((free_b + cached) * 0.9);
+        budget = (uint64_t)((free_b + cached) * 0.94);
         // free memory jitters by a few MB between calls; plan for the retired arena when it is about the size the
         // budget asks for, so that it is reused instead of being freed and allocated again (hundreds of ms at >100 GB)
         if (cached && budget > cached && cached >= budget - budget / 8) budget = cached;
