@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--columns", type=int, default=None, help="variant sites per window (one step sweeps one window)")
     ap.add_argument("--max-coverage", type=int, default=15)
     ap.add_argument("--haps", type=int, default=88)
-    ap.add_argument("--cpu-sample-cols", type=int, default=40)
+    ap.add_argument("--cpu-sample-cols", type=int, default=240)   # ~10 s of CPU work per sample on 16 host cores
     ap.add_argument("--cpu-sample-cov", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
