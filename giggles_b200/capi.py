@@ -273,6 +273,20 @@ def hmm_run_batch(problems, device: int = -1, budget: int = 0, precision: int = 
     return res
 
 
+def hmm_run_many(problems, device: int = -1, workers: int = 4, precision: int = 0):
+    """Independent chains run CONCURRENTLY on one device, one ``gg_hmm_run`` per host thread (ctypes releases the GIL;
+    every call has its own stream).  Meant for small chains — all-haplotagged chromosomes are one persistent CTA each,
+    so one chain occupies one SM of 148 — where it overlaps the host planning of some chains with the sweeps of others;
+    chains whose columns fill HBM should go through :func:`hmm_run_batch` (one after the other) instead.
+    Results are identical to one call per chain, in the same order."""
+    from concurrent.futures import ThreadPoolExecutor
+    cps = [p if isinstance(p, CProblem) else CProblem(p) for p in problems]
+    if not cps:
+        return []
+    with ThreadPoolExecutor(max_workers=max(1, min(workers, len(cps)))) as ex:
+        return list(ex.map(lambda cp: hmm_run(cp, device=device, precision=precision), cps))
+
+
 class Hmm:
     """Staged form: ``create`` (plan + H2D), ``sweep`` (device only), ``fetch`` (D2H)."""
 

@@ -72,47 +72,80 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
 };
 
-// One retired arena per device is kept for the next gg_hmm_create (cudaMalloc/cudaFree of a >100 GB arena costs
-// more than a sweep of a small window); gg_arena_release() frees it.
+// Retired arenas are kept for the next gg_hmm_create (cudaMalloc/cudaFree of a >100 GB arena costs more than a sweep
+// of a small window, and cudaFree synchronises the device, which would serialise chains that run concurrently from
+// several host threads).  Per key (2*device = state arena, 2*device+1 = table arena): at most ONE large arena — a
+// request it does not fit frees it first, there is no room for two — and a small pool of arenas of up to 4 GB for
+// concurrent small chains (all-haplotagged chromosomes).  gg_arena_release() frees everything.
 struct ArenaCache {
+    static constexpr size_t kSmallArena = (size_t)4 << 30, kSmallPoolBytes = (size_t)24 << 30, kSmallPoolCount = 64;
+    struct Ent { unsigned char *p; size_t n; };
     std::mutex mu;
-    std::map<int, std::pair<unsigned char *, size_t>> slot;
-    // two slots per device: key = 2*device (state arena) or 2*device+1 (table arena)
-    unsigned char *take(int dev, size_t need, size_t &got) {
+    std::map<int, std::vector<Ent>> pool;
+    static bool fits(size_t n, size_t need) { return n >= need && n <= need + need / 2 + (64u << 20); }
+    unsigned char *take(int key, size_t need, size_t &got) {
         std::lock_guard<std::mutex> g(mu);
-        auto it = slot.find(dev);
-        if (it == slot.end()) return nullptr;
-        unsigned char *p = it->second.first;
-        size_t n = it->second.second;
-        slot.erase(it);
-        if (n >= need && n <= need + need / 2 + (64u << 20)) {
-            got = n;
-            return p;
+        std::vector<Ent> &v = pool[key];
+        size_t best = v.size();
+        for (size_t i = 0; i < v.size(); ++i)
+            if (fits(v[i].n, need) && (best == v.size() || v[i].n < v[best].n)) best = i;
+        if (best != v.size()) {
+            Ent e = v[best];
+            v.erase(v.begin() + best);
+            got = e.n;
+            return e.p;
         }
-        cudaFree(p);
+        if (need > kSmallArena) {          // a large request needs the room: drop whatever is cached under this key
+            for (Ent &e : v) cudaFree(e.p);
+            v.clear();
+        }
         return nullptr;
     }
-    size_t cached(int dev) {
+    // what default_budget may count as free again: the large cached arena (or the largest cached one)
+    size_t cached(int key) {
         std::lock_guard<std::mutex> g(mu);
-        auto it = slot.find(dev);
-        return it == slot.end() ? 0 : it->second.second;
+        size_t m = 0;
+        for (const Ent &e : pool[key]) m = std::max(m, e.n);
+        return m;
     }
-    void give(int dev, unsigned char *p, size_t n) {
+    void give(int key, unsigned char *p, size_t n) {
         std::lock_guard<std::mutex> g(mu);
-        auto it = slot.find(dev);
-        if (it != slot.end()) {
-            cudaFree(it->second.first);
-            slot.erase(it);
+        std::vector<Ent> &v = pool[key];
+        if (n > kSmallArena) {             // keep one large arena only
+            for (size_t i = 0; i < v.size();)
+                if (v[i].n > kSmallArena) { cudaFree(v[i].p); v.erase(v.begin() + i); } else ++i;
         }
-        slot[dev] = {p, n};
+        v.push_back({p, n});
+        size_t small_bytes = 0, small_count = 0;
+        for (const Ent &e : v)
+            if (e.n <= kSmallArena) { small_bytes += e.n; ++small_count; }
+        for (size_t i = 0; i < v.size() && (small_bytes > kSmallPoolBytes || small_count > kSmallPoolCount);) {
+            if (v[i].n <= kSmallArena) {   // oldest first
+                small_bytes -= v[i].n; --small_count;
+                cudaFree(v[i].p);
+                v.erase(v.begin() + i);
+            } else ++i;
+        }
     }
     void clear() {
         std::lock_guard<std::mutex> g(mu);
-        for (auto &kv : slot) cudaFree(kv.second.first);
-        slot.clear();
+        for (auto &kv : pool)
+            for (Ent &e : kv.second) cudaFree(e.p);
+        pool.clear();
     }
 };
 static ArenaCache g_arena_cache;
+
+// cudaMalloc that gives the cached arenas back to the driver and tries once more before reporting out-of-memory
+static cudaError_t device_alloc(unsigned char **p, size_t n) {
+    cudaError_t e = cudaMalloc(p, n);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        g_arena_cache.clear();
+        e = cudaMalloc(p, n);
+    }
+    return e;
+}
 
 // cudaFuncSetAttribute is per device: remember which (device, kernel family) pairs have been configured
 static bool first_time_on_device(int device, int family) {
@@ -655,7 +688,7 @@ struct Engine {
         const size_t need = off + 256;
         h->tables = g_arena_cache.take(2 * h->device + 1, need, h->tables_bytes);
         if (!h->tables) {
-            GG_CUDA(cudaMalloc(&h->tables, need));
+            GG_CUDA(device_alloc(&h->tables, need));
             h->tables_bytes = need;
         }
         unsigned char *tb = h->tables;
@@ -679,7 +712,7 @@ struct Engine {
         GG_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned int), h->stream));
         h->arena = g_arena_cache.take(2 * h->device, h->sched.arena_bytes, h->arena_bytes);
         if (!h->arena && h->sched.arena_bytes) {
-            GG_CUDA(cudaMalloc(&h->arena, h->sched.arena_bytes));
+            GG_CUDA(device_alloc(&h->arena, h->sched.arena_bytes));
             h->arena_bytes = h->sched.arena_bytes;
         }
         // test hook: GG_POISON_ARENA=1 fills the state arena with NaN bit patterns so that any read of a value the

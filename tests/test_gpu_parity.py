@@ -327,3 +327,16 @@ def test_l2_lookahead_is_a_pure_hint():
         assert out.returncode == 0, out.stderr[-2000:]
         digests.add(out.stdout.strip().splitlines()[-1])
     assert len(digests) == 1
+
+
+def test_concurrent_chains_match_single_runs():
+    """capi.hmm_run_many: independent chains swept concurrently from host threads (own stream each, pooled arenas)
+    give bit-identical posteriors to one call per chain, in order."""
+    probs = [make_problem(n_columns=30 + 7 * i, n_haps=[8, 12, 88, 10, 33, 88][i % 6], coverage=5, max_coverage=[0, 4, 3, 6, 4, 0][i % 6] or 1,
+                          read_len_mean=1500, tags=["all", "none", "mixed"][i % 3], seed=900 + i) for i in range(12)]
+    single = [capi.hmm_run(p, device=0).values for p in probs]
+    for workers in (3, 8):
+        many = capi.hmm_run_many(probs, device=0, workers=workers)
+        assert len(many) == len(probs)
+        for a, b in zip(single, many):
+            assert np.array_equal(a, b.values)
