@@ -261,7 +261,8 @@ def hmm_run(p: Problem | CProblem, device: int = -1, budget: int = 0, precision:
 
 
 def hmm_run_batch(problems, device: int = -1, budget: int = 0, precision: int = 0, kernel_variant: int = 0):
-    """``gg_hmm_run_batch``: independent chains back to back, host planning of chain i+1 overlapped with the sweep of i."""
+    """``gg_hmm_run_batch``: independent chains on one device — small chains side by side, HBM-filling ones one at a
+    time with the planning of the next overlapped."""
     cps = [p if isinstance(p, CProblem) else CProblem(p) for p in problems]
     arr = (gg_problem * len(cps))(*[cp.struct for cp in cps])
     outs = (C.c_void_p * len(cps))()
@@ -275,10 +276,10 @@ def hmm_run_batch(problems, device: int = -1, budget: int = 0, precision: int = 
 
 def hmm_run_many(problems, device: int = -1, workers: int = 4, precision: int = 0):
     """Independent chains run CONCURRENTLY on one device, one ``gg_hmm_run`` per host thread (ctypes releases the GIL;
-    every call has its own stream).  Meant for small chains — all-haplotagged chromosomes are one persistent CTA each,
-    so one chain occupies one SM of 148 — where it overlaps the host planning of some chains with the sweeps of others;
-    chains whose columns fill HBM should go through :func:`hmm_run_batch` (one after the other) instead.
-    Results are identical to one call per chain, in the same order."""
+    every call has its own stream) — the same thing :func:`hmm_run_batch` does inside the library with its own
+    threads, for callers that already have a thread per chromosome.  Meant for small chains (all-haplotagged
+    chromosomes are one persistent CTA each); chains whose columns fill HBM must not overlap and belong in
+    :func:`hmm_run_batch`.  Results are identical to one call per chain, in the same order."""
     from concurrent.futures import ThreadPoolExecutor
     cps = [p if isinstance(p, CProblem) else CProblem(p) for p in problems]
     if not cps:

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -17,8 +18,10 @@
 #include <memory>
 #include <mutex>
 #include <set>
+#include <shared_mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -135,6 +138,8 @@ struct ArenaCache {
     }
 };
 static ArenaCache g_arena_cache;
+static std::mutex g_budget_mu;
+static std::map<int, uint64_t> g_last_queried_budget;   // per device: what the last cudaMemGetInfo-based budget was
 
 // cudaMalloc that gives the cached arenas back to the driver and tries once more before reporting out-of-memory
 static cudaError_t device_alloc(unsigned char **p, size_t n) {
@@ -841,8 +846,40 @@ static uint64_t default_budget(const gg_options *o, int device) {
         // free memory jitters by a few MB between calls; plan for the retired arena when it is about the size the
         // budget asks for, so that it is reused instead of being freed and allocated again (hundreds of ms at >100 GB)
         if (cached && budget > cached && cached >= budget - budget / 8) budget = cached;
+        std::lock_guard<std::mutex> g(g_budget_mu);
+        g_last_queried_budget[device] = budget;
     }
     return budget;
+}
+
+static void hmm_schedule(gg_hmm *h, uint64_t budget);
+
+// Schedule `h` under the caller's budget or the default one.  cudaMemGetInfo takes a driver-wide lock and was seen to
+// cost 5-75 ms now and then, more than the rest of gg_hmm_create together, so it is asked only when it can change the
+// outcome: not when the retired arena already holds the whole problem without recomputation, and not when that arena
+// IS the last default budget (there is nothing more to get).
+static void schedule_default(gg_hmm *h, const gg_options *o, int device) {
+    if (o && o->state_budget_bytes) {
+        hmm_schedule(h, o->state_budget_bytes);
+        return;
+    }
+    const uint64_t cached = g_arena_cache.cached(2 * device);
+    if (cached) {
+        uint64_t last = 0;
+        {
+            std::lock_guard<std::mutex> g(g_budget_mu);
+            auto it = g_last_queried_budget.find(device);
+            if (it != g_last_queried_budget.end()) last = it->second;
+        }
+        bool ok = true;
+        try {
+            hmm_schedule(h, cached);
+        } catch (const std::exception &) {
+            ok = false;                      // does not fit the retired arena at all: ask the driver
+        }
+        if (ok && (h->sched.levels <= 1 || (last && cached >= last - last / 8))) return;
+    }
+    hmm_schedule(h, default_budget(o, device));
 }
 
 static void need_device(const gg_options *o, int *device, int *num_sms) {
@@ -897,11 +934,20 @@ int gg_hmm_create(const gg_problem *p, const gg_options *o, gg_hmm **out, char *
     gg_hmm *h = nullptr;
     int rc = guarded(err, errlen, [&] {
         if (!p || !out) throw std::runtime_error("gg_hmm_create: null argument");
+        const auto t0 = std::chrono::steady_clock::now();
+        auto ms = [&] { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
         h = hmm_plan(p, o);          // validates the problem before any device work
+        const float t1 = ms();
         int device = 0, num_sms = 0;
         need_device(o, &device, &num_sms);
-        hmm_schedule(h, default_budget(o, device));
+        const float t2 = ms();
+        const float t3 = ms();
+        schedule_default(h, o, device);
+        const float t4 = ms();
         hmm_create_device(h, device, num_sms);
+        if (std::getenv("GG_TRACE"))
+            std::fprintf(stderr, "[gg create] plan %.2f ms, device query %.2f, (%.2f) budget + schedule %.2f, device tables/arena/uploads %.2f\n",
+                         t1, t2 - t1, t3 - t2, t4 - t3, ms() - t4);
     });
     if (rc != GG_OK) {
         delete h;
@@ -992,53 +1038,76 @@ int gg_hmm_run_batch(const gg_problem *problems, uint32_t n, const gg_options *o
     return guarded(err, errlen, [&] {
         if ((!problems || !results) && n) throw std::runtime_error("gg_hmm_run_batch: null argument");
         if (n == 0) return;
-        gg_hmm *first = hmm_plan(&problems[0], o);
-        std::unique_ptr<gg_hmm> cur(first);
+        std::unique_ptr<gg_hmm> first(hmm_plan(&problems[0], o));   // a malformed first chain is reported before any device work
         int device = 0, num_sms = 0;
         need_device(o, &device, &num_sms);
         const uint64_t budget = default_budget(o, device);
-        hmm_schedule(cur.get(), budget);
-        for (uint32_t i = 0; i < n; ++i) {
-            std::future<gg_hmm *> next;
-            if (i + 1 < n)
-                next = std::async(std::launch::async, [&, i] {
-                    gg_hmm *h = hmm_plan(&problems[i + 1], o);
-                    try { hmm_schedule(h, budget); } catch (...) { delete h; throw; }
-                    return h;
-                });
-            char e2[512] = {0};
-            int rc = GG_OK;
-            const bool trace = std::getenv("GG_TRACE") != nullptr;
-            const auto t0 = std::chrono::steady_clock::now();
-            auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t).count(); };
-            try {
-                hmm_create_device(cur.get(), device, num_sms);
-            } catch (...) {
-                if (next.valid()) { try { delete next.get(); } catch (...) {} }
-                throw;
+        // A few host threads take chains off a counter; each plans and schedules its chain (host only), then does the
+        // device part.  Chains whose state arena is small (all-haplotagged chromosomes: one persistent CTA each) hold a
+        // SHARED lock and therefore run side by side, each on its own stream; a chain that needs a large arena takes
+        // the lock exclusively — there is room for one such arena — while the other threads go on planning the chains
+        // behind it, so their host work stays hidden behind its sweep as before.  GG_BATCH_THREADS overrides the
+        // thread count (1 = strictly one chain after the other).
+        unsigned workers = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        if (const char *e = std::getenv("GG_BATCH_THREADS")) workers = (unsigned)std::max(1, std::atoi(e));
+        workers = std::min<unsigned>(workers, n);
+        const bool trace = std::getenv("GG_TRACE") != nullptr;
+        std::atomic<uint32_t> next{0};
+        std::atomic<bool> failed{false};
+        std::shared_mutex device_gate;
+        std::mutex err_mu;
+        int first_rc = GG_OK;
+        uint32_t first_chain = 0;
+        std::string first_msg;
+        auto record = [&](uint32_t i, int rc, const std::string &m) {
+            std::lock_guard<std::mutex> g(err_mu);
+            if (!failed.load() || i < first_chain) {
+                first_rc = rc;
+                first_chain = i;
+                first_msg = m;
             }
-            const float t_dev = ms_since(t0);
-            rc = gg_hmm_sweep(cur.get(), 0, e2, sizeof(e2));
-            const float t_sweep = ms_since(t0);
-            if (rc == GG_OK) rc = gg_hmm_fetch(cur.get(), &results[i], e2, sizeof(e2));
-            const float t_fetch = ms_since(t0);
+            failed.store(true);
+        };
+        auto work = [&] {
             cudaSetDevice(device);
-            const float host_ms = cur->stats.create_total_ms;
-            cur.reset();                       // the arena goes back to the cache for the next chain
-            const float t_destroy = ms_since(t0);
-            gg_hmm *nh = nullptr;
-            if (next.valid()) {
-                try { nh = next.get(); } catch (...) { if (rc == GG_OK) throw; }
+            for (;;) {
+                const uint32_t i = next.fetch_add(1);
+                if (i >= n || failed.load()) break;
+                std::unique_ptr<gg_hmm> h;
+                try {
+                    const auto t0 = std::chrono::steady_clock::now();
+                    auto ms_since = [&] { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+                    if (i == 0) h = std::move(first);          // only one thread draws chain 0
+                    else h.reset(hmm_plan(&problems[i], o));
+                    hmm_schedule(h.get(), budget);
+                    const float t_plan = ms_since();
+                    const bool large = h->sched.arena_bytes > ArenaCache::kSmallArena;
+                    std::unique_lock<std::shared_mutex> excl(device_gate, std::defer_lock);
+                    std::shared_lock<std::shared_mutex> shar(device_gate, std::defer_lock);
+                    if (large) excl.lock(); else shar.lock();
+                    const float t_gate = ms_since();
+                    hmm_create_device(h.get(), device, num_sms);
+                    char e2[512] = {0};
+                    int rc = gg_hmm_sweep(h.get(), 0, e2, sizeof(e2));
+                    if (rc == GG_OK) rc = gg_hmm_fetch(h.get(), &results[i], e2, sizeof(e2));
+                    cudaSetDevice(device);
+                    h.reset();                 // the arena goes back to the cache before the gate opens
+                    if (trace)
+                        std::fprintf(stderr, "[gg batch] chain %u: plan+schedule %.1f ms, waited %.1f ms for the device, device part %.1f ms (%s arena)\n",
+                                     i, t_plan, t_gate - t_plan, ms_since() - t_gate, large ? "large" : "small");
+                    if (rc != GG_OK) record(i, rc, e2);
+                } catch (const CudaError &e) {
+                    record(i, e.status, e.what());
+                } catch (const std::exception &e) {
+                    record(i, GG_ERR_INVALID, e.what());
+                }
             }
-            if (trace)
-                std::fprintf(stderr, "[gg batch] chain %u: device-create %.1f ms, sweep %.1f, fetch %.1f, destroy %.1f, wait-for-next-plan %.1f (its host work %.1f)\n",
-                             i, t_dev, t_sweep - t_dev, t_fetch - t_sweep, t_destroy - t_fetch, ms_since(t0) - t_destroy, host_ms);
-            if (rc != GG_OK) {
-                delete nh;
-                throw CudaError(rc, std::string("chain ") + std::to_string(i) + ": " + e2);
-            }
-            cur.reset(nh);
-        }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned w = 1; w < workers; ++w) pool.emplace_back(work);
+        work();
+        for (std::thread &t : pool) t.join();
+        if (failed.load()) throw CudaError(first_rc, std::string("chain ") + std::to_string(first_chain) + ": " + first_msg);
     });
 }
 

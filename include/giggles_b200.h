@@ -111,11 +111,13 @@ typedef struct gg_stats {
 int gg_hmm_run(const gg_problem *p, const gg_options *o, gg_result **out,
                char *err, size_t errlen);
 
-/* ---- many chains (chromosomes) on one device, back to back: what the per-chromosome loop of
- *      giggles/cli/genotype.py:196-338 does one GenotypeHMM at a time.  The column plan and checkpoint schedule of
- *      chain i+1 are built on a host thread while the device sweeps chain i.  results[i] is chain i's
- *      result (caller frees each); on failure the status of the first failing chain is returned, results of the
- *      chains before it stay valid, the rest are NULL. */
+/* ---- many chains (chromosomes) on one device: what the per-chromosome loop of giggles/cli/genotype.py:196-338
+ *      does one GenotypeHMM at a time.  A few host threads plan and schedule the chains; chains whose
+ *      state fits a small arena (all-haplotagged chromosomes: one persistent CTA each) are swept side by side, each
+ *      on its own stream; a chain that needs most of HBM has the device to itself while the chains behind it are
+ *      being planned.  GG_BATCH_THREADS=1 runs strictly one chain after the other.  results[i] is chain i's result
+ *      (the caller frees every non-NULL entry); on failure the status and message of the lowest-numbered failing
+ *      chain are returned and results[i] is NULL for chains that failed or were not run. */
 int gg_hmm_run_batch(const gg_problem *problems, uint32_t n, const gg_options *o, gg_result **results,
                      char *err, size_t errlen);
 

@@ -152,6 +152,20 @@ def test_batch_of_chains_matches_single_runs():
     for a, b in zip(singles, batch):
         assert np.array_equal(a, b.values)
     assert capi.hmm_run_batch([], device=0) == []
+    # a malformed chain in the middle: its status and number come back, whatever the other chains did meanwhile
+    import copy
+    bad = copy.copy(probs[2])
+    bad.n_alleles = probs[2].n_alleles.copy()
+    bad.n_alleles[1] = 40
+    with pytest.raises(capi.GGError) as ei:
+        capi.hmm_run_batch(probs[:2] + [bad] + probs[3:], device=0)
+    assert ei.value.status == capi.GG_ERR_INVALID and "chain 2" in str(ei.value)
+    # more chains than worker threads, sizes far apart (small tagged chains next to windows that take GBs)
+    many = [make_problem(20 + (7 * i) % 50, 88, coverage=6, max_coverage=[0, 0, 9, 0][i % 4] or 1, read_len_mean=2500,
+                         tags=["all", "all", "none", "all"][i % 4], seed=700 + i, window=True) for i in range(40)]
+    res = capi.hmm_run_batch(many, device=0)
+    for p, r in zip(many, res):
+        assert np.array_equal(capi.hmm_run(p, device=0).values, r.values)
 
 
 def test_single_column_and_empty_problem():

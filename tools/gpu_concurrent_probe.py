@@ -12,8 +12,9 @@ probs = [capi.CProblem(synth.config2_window(cols, seed=10 + i, tags="all")) for 
 capi.hmm_run(probs[0], device=0)
 t = time.perf_counter(); r1 = [capi.hmm_run(p, device=0) for p in probs]; t1 = time.perf_counter() - t
 print(f"{n} chains x {cols} tagged columns: sequential {1e3*t1:.1f} ms = {n*cols/t1:,.0f} variants/s", flush=True)
+capi.hmm_run_batch(probs, device=0)
 t = time.perf_counter(); rb = capi.hmm_run_batch(probs, device=0); tb = time.perf_counter() - t
-print(f"  gg_hmm_run_batch {1e3*tb:.1f} ms = {n*cols/tb:,.0f} variants/s", flush=True)
+print(f"  gg_hmm_run_batch {1e3*tb:.1f} ms = {n*cols/tb:,.0f} variants/s, identical {all(np.array_equal(a.values, b.values) for a, b in zip(r1, rb))}", flush=True)
 for w in (2, 4, 8, 16, 24):
     capi.hmm_run_many(probs, device=0, workers=w)      # warm the arena pool for this width
     t = time.perf_counter(); r2 = capi.hmm_run_many(probs, device=0, workers=w); t2 = time.perf_counter() - t
