@@ -1,7 +1,8 @@
 """ctypes binding of the C ABI (include/giggles_b200.h) -> libgiggles_b200.so.
 
-This is the reference-side stub a maintainer would write in Python; the Cython
-surface (giggles_b200/core.pyx) binds the same entry points from C++.  There is
+This is the reference-side stub a maintainer would write in Python; the drop-in
+C++ class (integration/genotypehmm.cpp, bound by the reference's own giggles/core.pyx)
+calls the same entry points.  There is
 no fallback: if the shared library is missing, importing :func:`lib` raises.
 """
 from __future__ import annotations
@@ -52,7 +53,11 @@ class gg_options(C.Structure):
         ("state_budget_bytes", C.c_uint64),
         ("precision", C.c_int32),
         ("kernel_variant", C.c_int32),
+        ("flags", C.c_uint32),
     ]
+
+
+GG_OPT_SHARED_ARENA = 1
 
 
 class gg_readset_view(C.Structure):
@@ -94,7 +99,7 @@ class gg_stats(C.Structure):
 # every symbol include/giggles_b200.h declares (tests check that the library exports them all)
 SYMBOLS = [
     "gg_hmm_run", "gg_hmm_run_batch", "gg_hmm_create", "gg_hmm_sweep", "gg_hmm_fetch", "gg_hmm_stats", "gg_hmm_destroy", "gg_arena_release", "gg_hmm_debug_scales", "gg_hmm_debug_op_times",
-    "gg_result_likelihoods", "gg_result_n_columns", "gg_result_flat", "gg_result_free", "gg_result_call", "gg_result_from_host",
+    "gg_result_likelihoods", "gg_result_n_columns", "gg_result_flat", "gg_result_free", "gg_result_reran_fp64", "gg_fp64_rerun_count", "gg_result_call", "gg_result_from_host",
     "gg_plan_build", "gg_plan_n_columns", "gg_plan_active", "gg_plan_untagged", "gg_plan_shared_mask_prev",
     "gg_plan_compatible_prev", "gg_plan_free",
     "gg_entry_emission", "gg_entry_emission_batch", "gg_transition_scalars", "gg_binomial_coefficient",
@@ -135,6 +140,8 @@ def lib() -> C.CDLL:
     L.gg_result_flat.restype = C.POINTER(dbl)
     L.gg_result_free.argtypes = [vp]
     L.gg_result_free.restype = None
+    L.gg_result_reran_fp64.argtypes = [vp]
+    L.gg_fp64_rerun_count.restype = u64
     L.gg_result_call.argtypes = [vp, dbl, C.POINTER(i32), C.POINTER(i32), C.POINTER(dbl)]
     L.gg_plan_build.argtypes = [C.POINTER(gg_problem), C.POINTER(vp)] + errargs
     L.gg_plan_n_columns.argtypes = [vp]
@@ -162,7 +169,7 @@ def lib() -> C.CDLL:
     L.gg_binomial_coefficient.argtypes = [i32, i32]
     L.gg_binomial_coefficient.restype = i32
     L.gg_schedule_dry_run.argtypes = [u32, C.POINTER(u64), C.POINTER(u64), u64, C.POINTER(u64), C.POINTER(u32),
-                                      C.POINTER(u64), C.POINTER(u64)] + errargs
+                                      C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)] + errargs
     L.gg_device_copy_gbs.argtypes = [C.c_int, u64, C.c_int]
     L.gg_device_copy_gbs.restype = dbl
     L.gg_version.restype = C.c_char_p
@@ -226,6 +233,7 @@ class Result:
         self.offsets = np.ctypeslib.as_array(offs, shape=(n + 1,)).copy() if n else np.zeros(1, np.uint64)
         total = int(self.offsets[-1])
         self.values = np.ctypeslib.as_array(flat, shape=(total,)).copy() if total else np.zeros(0)
+        self.reran_fp64 = bool(L.gg_result_reran_fp64(handle))
 
     def column(self, c: int) -> np.ndarray:
         return self.values[int(self.offsets[c]):int(self.offsets[c + 1])]
@@ -245,8 +253,8 @@ class Result:
             self._h = None
 
 
-def _options(device=-1, budget=0, precision=0, kernel_variant=0):
-    return gg_options(int(device), int(budget), int(precision), int(kernel_variant))
+def _options(device=-1, budget=0, precision=0, kernel_variant=0, flags=0):
+    return gg_options(int(device), int(budget), int(precision), int(kernel_variant), int(flags))
 
 
 def hmm_run(p: Problem | CProblem, device: int = -1, budget: int = 0, precision: int = 0,
@@ -292,11 +300,11 @@ class Hmm:
     """Staged form: ``create`` (plan + H2D), ``sweep`` (device only), ``fetch`` (D2H)."""
 
     def __init__(self, p: Problem | CProblem, device: int = -1, budget: int = 0, precision: int = 0,
-                 kernel_variant: int = 0):
+                 kernel_variant: int = 0, shared_arena: bool = False):
         self.cp = p if isinstance(p, CProblem) else CProblem(p)
         err = C.create_string_buffer(512)
         self._h = C.c_void_p()
-        o = _options(device, budget, precision, kernel_variant)
+        o = _options(device, budget, precision, kernel_variant, GG_OPT_SHARED_ARENA if shared_arena else 0)
         _check(lib().gg_hmm_create(C.byref(self.cp.struct), C.byref(o), C.byref(self._h), err, len(err)), err)
 
     def sweep(self, timed_kernels: bool = False) -> None:
@@ -411,9 +419,9 @@ def pyset_replay(ops, cap: int) -> list:
 def schedule_dry_run(col_bytes, fg_bytes, budget):
     cb = np.ascontiguousarray(col_bytes, dtype=np.uint64)
     fb = np.ascontiguousarray(fg_bytes, dtype=np.uint64)
-    arena, levels, nb, nf = C.c_uint64(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+    arena, levels, nb, nf, bb = C.c_uint64(), C.c_uint32(), C.c_uint64(), C.c_uint64(), C.c_uint64()
     err = C.create_string_buffer(512)
     rc = lib().gg_schedule_dry_run(cb.size, as_ptr(cb, C.c_uint64), as_ptr(fb, C.c_uint64), int(budget),
-                                   C.byref(arena), C.byref(levels), C.byref(nb), C.byref(nf), err, len(err))
+                                   C.byref(arena), C.byref(levels), C.byref(nb), C.byref(nf), C.byref(bb), err, len(err))
     _check(rc, err)
-    return dict(arena_bytes=arena.value, levels=levels.value, n_bwd=nb.value, n_fwd=nf.value)
+    return dict(arena_bytes=arena.value, levels=levels.value, n_bwd=nb.value, n_fwd=nf.value, bwd_col_bytes=bb.value)

@@ -110,6 +110,7 @@ const double *gg_result_flat(const gg_result *r, const uint64_t **offsets) {
 }
 
 void gg_result_free(gg_result *r) { delete r; }
+int gg_result_reran_fp64(const gg_result *r) { return r && r->reran_fp64 ? 1 : 0; }
 
 gg_result *gg_result_from_host(uint32_t n_columns, const uint64_t *offsets, const double *values) {
     gg_result *r = new gg_result();
@@ -188,7 +189,8 @@ int32_t gg_binomial_coefficient(int32_t n, int32_t k) {
 
 // ---- schedule dry run (host only; used by the CPU tests) -----------------------------------------
 int gg_schedule_dry_run(uint32_t n_columns, const uint64_t *col_bytes, const uint64_t *fg_bytes, uint64_t budget,
-                        uint64_t *arena_bytes, uint32_t *levels, uint64_t *n_bwd, uint64_t *n_fwd, char *err, size_t errlen) {
+                        uint64_t *arena_bytes, uint32_t *levels, uint64_t *n_bwd, uint64_t *n_fwd, uint64_t *bwd_col_bytes,
+                        char *err, size_t errlen) {
     try {
         std::vector<uint64_t> cb(col_bytes, col_bytes + n_columns), fb(fg_bytes, fg_bytes + n_columns);
         gg::Schedule s;
@@ -198,6 +200,7 @@ int gg_schedule_dry_run(uint32_t n_columns, const uint64_t *col_bytes, const uin
         if (levels) *levels = s.levels;
         if (n_bwd) *n_bwd = s.n_bwd;
         if (n_fwd) *n_fwd = s.n_fwd;
+        if (bwd_col_bytes) *bwd_col_bytes = s.bwd_col_bytes;
         return GG_OK;
     } catch (const std::exception &e) {
         set_err(err, errlen, e.what());

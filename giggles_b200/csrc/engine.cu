@@ -138,6 +138,31 @@ struct ArenaCache {
     }
 };
 static ArenaCache g_arena_cache;
+
+// One state arena per device shared by every handle created with GG_OPT_SHARED_ARENA: such a handle holds its tables
+// only and borrows the arena for the duration of a sweep (sweeps of these handles are serialised by the lock).  This
+// is how many chromosomes stay planned and resident on one device while the state memory - which a single chain of
+// HBM-filling columns needs whole - exists once.  Grows on demand, never shrinks until gg_arena_release().
+struct SharedArena {
+    std::mutex mu;
+    unsigned char *p = nullptr;
+    size_t n = 0;
+};
+static std::mutex g_shared_mu;
+static std::map<int, std::unique_ptr<SharedArena>> g_shared_arenas;
+static SharedArena &shared_arena_of(int device) {
+    std::lock_guard<std::mutex> g(g_shared_mu);
+    std::unique_ptr<SharedArena> &sa = g_shared_arenas[device];
+    if (!sa) sa.reset(new SharedArena());
+    return *sa;
+}
+static std::atomic<uint64_t> g_fp64_reruns{0};      // fp32 range guard: chains rerun on fp64 state (process-wide)
+static bool all_finite(const gg_result *r) {
+    if (r)
+        for (double v : r->values)
+            if (!std::isfinite(v)) return false;
+    return true;
+}
 static std::mutex g_budget_mu;
 static std::map<int, uint64_t> g_last_queried_budget;   // per device: what the last cudaMemGetInfo-based budget was
 
@@ -152,12 +177,18 @@ static cudaError_t device_alloc(unsigned char **p, size_t n) {
     return e;
 }
 
-// cudaFuncSetAttribute is per device: remember which (device, kernel family) pairs have been configured
-static bool first_time_on_device(int device, int family) {
+// cudaFuncSetAttribute is per device.  Runs `configure` exactly once per (device, kernel family) and holds every other
+// caller back until it has finished: a thread that merely saw "already started" could otherwise launch (or ask for an
+// occupancy figure) with more than 48 KB of dynamic shared memory before the attribute is set (cold process, several
+// host threads: gg_hmm_run_batch workers, capi.hmm_run_many).  A failed configuration is retried by the next caller.
+template <typename F>
+static void configure_once(int device, int family, F &&configure) {
     static std::mutex mu;
-    static std::set<std::pair<int, int>> seen;
+    static std::set<std::pair<int, int>> done;
     std::lock_guard<std::mutex> g(mu);
-    return seen.insert({device, family}).second;
+    if (done.count({device, family})) return;
+    configure();
+    done.insert({device, family});
 }
 
 struct LaunchShape {
@@ -173,6 +204,7 @@ struct gg_hmm {
     Plan plan;
     Schedule sched;
     bool fp64 = false;
+    bool shared_arena = false;   // GG_OPT_SHARED_ARENA: the state arena is borrowed per sweep
     int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined, never two CTAs per SM, 3 = pipelined, never 16 consumer warps, 4 = no chain kernel, 5 = no warp-per-block kernel
     int device = 0;
     int num_sms = 0;
@@ -182,7 +214,7 @@ struct gg_hmm {
     std::vector<ColDesc> host_cols;
     DevBuf<ColDesc> d_cols;
     DevBuf<uint8_t> d_em_side, d_allele1;
-    DevBuf<double> d_em_prob, d_scale_a, d_scale_b, d_result;
+    DevBuf<double> d_em_prob, d_scale_a, d_scale_b, d_result, d_emax;
     DevBuf<uint16_t> d_row_order;
     DevBuf<unsigned char> d_partial;
     unsigned char *arena = nullptr;      // state arena (columns, F/G tables)
@@ -203,10 +235,15 @@ struct gg_hmm {
     std::vector<cudaEvent_t> ev;   // timing events (timed sweeps only)
     std::vector<float> op_ms;      // per-op durations of the last timed sweep
     ~gg_hmm() {
+        // work queued on the stream (a sweep that failed half-way, a caller that destroys after an error) may still
+        // use the arenas: drain it before another handle can take them from the cache; after a device error they are
+        // freed instead of being cached
+        const bool clean = !stream || cudaStreamSynchronize(stream) == cudaSuccess;
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
-        if (arena) g_arena_cache.give(2 * device, arena, arena_bytes);
-        if (tables) g_arena_cache.give(2 * device + 1, tables, tables_bytes);
+        if (arena && !shared_arena) { if (clean) g_arena_cache.give(2 * device, arena, arena_bytes); else cudaFree(arena); }
+        if (tables) { if (clean) g_arena_cache.give(2 * device + 1, tables, tables_bytes); else cudaFree(tables); }
+        if (!clean) cudaGetLastError();
     }
 };
 
@@ -419,7 +456,7 @@ struct Engine {
         if (sizeof(T) != 4 || h->kernel_variant == 1 || a.in == nullptr) return false;
         const int V = h->shape.V, NS = h->shape.NS;
         if (V < 2 || a.R > 512) return false;
-        if (first_time_on_device(h->device, 1)) {
+        configure_once(h->device, 1, [] {
             for (int vv : {2, 4})
                 for (uint32_t g = 1; g <= 32; g <<= 1)
                     for (bool f : {false, true})
@@ -429,7 +466,7 @@ struct Engine {
                                     for (bool tw : {false, true})
                                         if (const void *kk = tma_kernel(f, vv, g, ns, mt, cwt, tw))
                                             GG_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
-        }
+        });
         const uint32_t rpi = 32 / a.G;
         const uint32_t nred = fwd ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
         const uint32_t ncls = pco.n_alleles + 1;
@@ -498,19 +535,30 @@ struct Engine {
         return true;
     }
 
+    // PASS 1 of the emission kernel for the columns of one EMIT op (tables scaled by the column maxima of PASS 0)
     static void launch_emit(gg_hmm *h, const Op &op) {
-        const Plan &pl = h->plan;
-        uint32_t lo = op.c;
         T *region = reinterpret_cast<T *>(h->arena + op.out_off);
-        const uint64_t prefix_lo = h->fg_prefix_elems[op.c];
-        while (lo <= op.hi) {
-            const uint32_t n = std::min<uint32_t>(op.hi - lo + 1, 32768);
+        launch_emission<1>(h, op.c, op.hi, region, h->fg_prefix_elems[op.c]);
+    }
+
+    // PASS 0 for every column: the per-column emission maxima (once per sweep, ~0.1 % of its bytes)
+    static void launch_emax(gg_hmm *h) {
+        const uint32_t C = h->plan.n_columns;
+        GG_CUDA(cudaMemsetAsync(h->d_emax.p, 0, (size_t)C * sizeof(double), h->stream));
+        launch_emission<0>(h, 0, C - 1, nullptr, 0);
+    }
+
+    template <int PASS>
+    static void launch_emission(gg_hmm *h, uint32_t lo, uint32_t hi, T *region, uint64_t prefix_lo) {
+        const Plan &pl = h->plan;
+        while (lo <= hi) {
+            const uint32_t n = std::min<uint32_t>(hi - lo + 1, 32768);
             uint32_t umax = 0;
             for (uint32_t c = lo; c < lo + n; ++c) umax = std::max(umax, pl.cols[c].u);
-            const uint64_t work = fg_elems(umax, pl.max_alleles);
+            const uint64_t work = (uint64_t)2 << umax;
             const uint32_t bx = (uint32_t)std::min<uint64_t>((work + 255) / 256, 2048);
-            emission_kernel<T><<<dim3(bx, n), 256, 0, h->stream>>>(h->d_cols.p, h->d_em_side.p, h->d_em_prob.p, region,
-                                                                   prefix_lo, lo);
+            emission_kernel<T, PASS><<<dim3(bx, n), 256, 0, h->stream>>>(h->d_cols.p, h->d_em_side.p, h->d_em_prob.p, region,
+                                                                         prefix_lo, lo, h->d_emax.p);
             GG_CUDA(cudaGetLastError());
             ++h->stats.n_launches;
             lo += n;
@@ -606,25 +654,26 @@ struct Engine {
         a.no_fast_posterior = h->kernel_variant == 6;
         const void *k = chain_kernel_ptr(run.fwd, (R + kChainWarps - 1) / kChainWarps);
         const uint32_t smem = chain_smem_bytes(R, run.max_classes, run.fwd);
-        if (first_time_on_device(h->device, 2)) {
+        configure_once(h->device, 2, [] {
             for (uint32_t n = 1; n <= (uint32_t)kChainMaxNIT; ++n)
                 for (bool f : {false, true})
                     GG_CUDA(cudaFuncSetAttribute(chain_kernel_ptr(f, n), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
-        }
+        });
         void *params[] = {(void *)&a};
         GG_CUDA(cudaLaunchKernel(k, dim3(1), dim3(kChainThreads), params, smem, h->stream));
         ++h->stats.n_launches;
     }
 
     static void set_attrs(int device) {
-        if (!first_time_on_device(device, sizeof(T) == 4 ? 3 : 4)) return;
-        for (int V : {1, 2, 4})
-            for (int NS : {1, 2, 4, 8})
-                for (bool fwd : {false, true}) {
-                    if (V == 4 && sizeof(T) != 4) continue;
-                    const void *k = pick_kernel<T>(V, NS, fwd);
-                    GG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-                }
+        configure_once(device, sizeof(T) == 4 ? 3 : 4, [] {
+            for (int V : {1, 2, 4})
+                for (int NS : {1, 2, 4, 8})
+                    for (bool fwd : {false, true}) {
+                        if (V == 4 && sizeof(T) != 4) continue;
+                        const void *k = pick_kernel<T>(V, NS, fwd);
+                        GG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+                    }
+        });
     }
 
     // ---- host half of gg_hmm_create: sizes, checkpoint schedule, run fusion.  No CUDA call: a worker thread can do it
@@ -687,6 +736,7 @@ struct Engine {
         const size_t o_ch = carve(h->chain_steps.size() * sizeof(ChainStep));
         const size_t o_sa = carve((size_t)C * sizeof(double));
         const size_t o_sb = carve((size_t)C * sizeof(double));
+        const size_t o_emax = carve((size_t)C * sizeof(double));
         const size_t o_res = carve((size_t)pl.gl_offsets[C] * sizeof(double));
         const size_t o_cnt = carve(sizeof(unsigned int));
         const size_t o_part = carve((size_t)h->max_grid * kPartialStride * sizeof(T));
@@ -705,6 +755,7 @@ struct Engine {
         h->d_chain_steps.bind(tb + o_ch, h->chain_steps.size());
         h->d_scale_a.bind(tb + o_sa, C);
         h->d_scale_b.bind(tb + o_sb, C);
+        h->d_emax.bind(tb + o_emax, C);
         h->d_result.bind(tb + o_res, pl.gl_offsets[C]);
         h->d_counter.bind(tb + o_cnt, 1);
         h->d_partial.bind(tb + o_part, (size_t)h->max_grid * kPartialStride * sizeof(T));
@@ -715,15 +766,14 @@ struct Engine {
         h->d_row_order.upload(pl.row_order, h->stream);
         h->d_chain_steps.upload(h->chain_steps, h->stream);
         GG_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned int), h->stream));
-        h->arena = g_arena_cache.take(2 * h->device, h->sched.arena_bytes, h->arena_bytes);
-        if (!h->arena && h->sched.arena_bytes) {
-            GG_CUDA(device_alloc(&h->arena, h->sched.arena_bytes));
-            h->arena_bytes = h->sched.arena_bytes;
+        if (!h->shared_arena) {
+            h->arena = g_arena_cache.take(2 * h->device, h->sched.arena_bytes, h->arena_bytes);
+            if (!h->arena && h->sched.arena_bytes) {
+                GG_CUDA(device_alloc(&h->arena, h->sched.arena_bytes));
+                h->arena_bytes = h->sched.arena_bytes;
+            }
+            poison_arena(h);
         }
-        // test hook: GG_POISON_ARENA=1 fills the state arena with NaN bit patterns so that any read of a value the
-        // schedule has not produced yet shows up in the posteriors
-        if (const char *poison = std::getenv("GG_POISON_ARENA"))
-            if (poison[0] == '1' && h->arena) GG_CUDA(cudaMemsetAsync(h->arena, 0xFF, h->arena_bytes, h->stream));
         GG_CUDA(cudaMemsetAsync(h->d_scale_a.p, 0, C * sizeof(double), h->stream));
         GG_CUDA(cudaMemsetAsync(h->d_scale_b.p, 0, C * sizeof(double), h->stream));
         if (pl.gl_offsets[C]) GG_CUDA(cudaMemsetAsync(h->d_result.p, 0, pl.gl_offsets[C] * sizeof(double), h->stream));
@@ -749,7 +799,41 @@ struct Engine {
         st.scheduled_bytes = sb;
     }
 
+    // test hook: GG_POISON_ARENA=1 fills the state arena with NaN bit patterns so that any read of a value the
+    // schedule has not produced yet shows up in the posteriors
+    static void poison_arena(gg_hmm *h) {
+        if (const char *poison = std::getenv("GG_POISON_ARENA"))
+            if (poison[0] == '1' && h->arena) GG_CUDA(cudaMemsetAsync(h->arena, 0xFF, h->arena_bytes, h->stream));
+    }
+
     static void sweep(gg_hmm *h, int timed) {
+        if (!h->shared_arena) {
+            sweep_with_arena(h, timed);
+            return;
+        }
+        SharedArena &sa = shared_arena_of(h->device);
+        std::lock_guard<std::mutex> g(sa.mu);
+        if (sa.n < h->sched.arena_bytes) {
+            if (sa.p) GG_CUDA(cudaFree(sa.p));
+            sa.p = nullptr;
+            sa.n = 0;
+            GG_CUDA(device_alloc(&sa.p, h->sched.arena_bytes));
+            sa.n = h->sched.arena_bytes;
+        }
+        h->arena = sa.p;
+        h->arena_bytes = h->sched.arena_bytes;
+        try {
+            poison_arena(h);               // whatever another chain left behind must not matter either
+            sweep_with_arena(h, timed);    // returns after the stream has drained
+        } catch (...) {
+            cudaStreamSynchronize(h->stream);
+            h->arena = nullptr;
+            throw;
+        }
+        h->arena = nullptr;
+    }
+
+    static void sweep_with_arena(gg_hmm *h, int timed) {
         gg_stats &st = h->stats;
         st.n_launches = 0;
         const std::vector<Op> &ops = h->exec_ops;
@@ -766,6 +850,7 @@ struct Engine {
             for (size_t i = old; i < h->ev.size(); ++i) GG_CUDA(cudaEventCreate(&h->ev[i]));
         }
         GG_CUDA(cudaEventRecord(h->ev[0], h->stream));
+        launch_emax(h);
         for (size_t i = 0; i < nops; ++i) {
             const Op &op = ops[i];
             if (per_kernel) GG_CUDA(cudaEventRecord(h->ev[2 + 2 * i], h->stream));
@@ -905,6 +990,7 @@ static gg_hmm *hmm_plan(const gg_problem *p, const gg_options *o) {
         h->stats.create_total_ms = h->stats.create_plan_ms;
         h->fp64 = o && o->precision == 1;
         h->kernel_variant = o ? o->kernel_variant : 0;
+        h->shared_arena = o && (o->flags & GG_OPT_SHARED_ARENA);
     } catch (...) {
         delete h;
         throw;
@@ -1000,7 +1086,16 @@ void gg_hmm_destroy(gg_hmm *h) {
     delete h;
 }
 
-void gg_arena_release(void) { g_arena_cache.clear(); }
+void gg_arena_release(void) {
+    g_arena_cache.clear();
+    std::lock_guard<std::mutex> g(g_shared_mu);
+    for (auto &kv : g_shared_arenas) {
+        std::lock_guard<std::mutex> g2(kv.second->mu);
+        if (kv.second->p) cudaFree(kv.second->p);
+        kv.second->p = nullptr;
+        kv.second->n = 0;
+    }
+}
 
 // STREAM-style device copy bandwidth (read + write bytes per second, best of `reps`), the same measurement that
 // defines the roofline denominator; lets a benchmark report what THIS device does on the day.
@@ -1068,34 +1163,79 @@ int gg_hmm_run_batch(const gg_problem *problems, uint32_t n, const gg_options *o
             }
             failed.store(true);
         };
+        // one chain on the device at the given precision; returns its status (results[i] set on success)
+        auto run_chain = [&](uint32_t i, std::unique_ptr<gg_hmm> h, const gg_options *oo, std::string &msg) -> int {
+            const auto t0 = std::chrono::steady_clock::now();
+            auto ms_since = [&] { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+            if (!h) h.reset(hmm_plan(&problems[i], oo));
+            hmm_schedule(h.get(), budget);
+            const float t_plan = ms_since();
+            bool large = h->sched.arena_bytes > ArenaCache::kSmallArena;
+            int rc = GG_OK;
+            float t_gate = 0.f;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                std::unique_lock<std::shared_mutex> excl(device_gate, std::defer_lock);
+                std::shared_lock<std::shared_mutex> shar(device_gate, std::defer_lock);
+                if (large) excl.lock(); else shar.lock();
+                t_gate = ms_since();
+                char e2[512] = {0};
+                try {
+                    if (!h->stream) hmm_create_device(h.get(), device, num_sms);
+                    rc = gg_hmm_sweep(h.get(), 0, e2, sizeof(e2));
+                    if (rc == GG_OK) rc = gg_hmm_fetch(h.get(), &results[i], e2, sizeof(e2));
+                    msg = e2;
+                } catch (const CudaError &e) {
+                    rc = e.status;
+                    msg = e.what();
+                }
+                if (rc == GG_ERR_NOMEM && !large && attempt == 0) {
+                    // small chains share the device and their arenas are not counted against each other: when one of
+                    // them runs out of memory, let it try again alone instead of failing the batch
+                    std::unique_ptr<gg_hmm> again(hmm_plan(&problems[i], oo));
+                    cudaSetDevice(device);
+                    h = std::move(again);
+                    hmm_schedule(h.get(), budget);
+                    large = true;
+                    continue;
+                }
+                cudaSetDevice(device);
+                h.reset();                 // the arena goes back to the cache before the gate opens
+                break;
+            }
+            if (trace)
+                std::fprintf(stderr, "[gg batch] chain %u: plan+schedule %.1f ms, waited %.1f ms for the device, device part %.1f ms (%s arena)\n",
+                             i, t_plan, t_gate - t_plan, ms_since() - t_gate, large ? "large" : "small");
+            return rc;
+        };
         auto work = [&] {
             cudaSetDevice(device);
             for (;;) {
                 const uint32_t i = next.fetch_add(1);
                 if (i >= n || failed.load()) break;
-                std::unique_ptr<gg_hmm> h;
                 try {
-                    const auto t0 = std::chrono::steady_clock::now();
-                    auto ms_since = [&] { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+                    std::string msg;
+                    std::unique_ptr<gg_hmm> h;
                     if (i == 0) h = std::move(first);          // only one thread draws chain 0
-                    else h.reset(hmm_plan(&problems[i], o));
-                    hmm_schedule(h.get(), budget);
-                    const float t_plan = ms_since();
-                    const bool large = h->sched.arena_bytes > ArenaCache::kSmallArena;
-                    std::unique_lock<std::shared_mutex> excl(device_gate, std::defer_lock);
-                    std::shared_lock<std::shared_mutex> shar(device_gate, std::defer_lock);
-                    if (large) excl.lock(); else shar.lock();
-                    const float t_gate = ms_since();
-                    hmm_create_device(h.get(), device, num_sms);
-                    char e2[512] = {0};
-                    int rc = gg_hmm_sweep(h.get(), 0, e2, sizeof(e2));
-                    if (rc == GG_OK) rc = gg_hmm_fetch(h.get(), &results[i], e2, sizeof(e2));
-                    cudaSetDevice(device);
-                    h.reset();                 // the arena goes back to the cache before the gate opens
-                    if (trace)
-                        std::fprintf(stderr, "[gg batch] chain %u: plan+schedule %.1f ms, waited %.1f ms for the device, device part %.1f ms (%s arena)\n",
-                                     i, t_plan, t_gate - t_plan, ms_since() - t_gate, large ? "large" : "small");
-                    if (rc != GG_OK) record(i, rc, e2);
+                    int rc = run_chain(i, std::move(h), o, msg);
+                    // the fp32 range guard of gg_hmm_run, per chain (one rerun on fp64 state, under the gate its
+                    // larger arena calls for)
+                    if (rc == GG_OK && !(o && o->precision == 1) && !all_finite(results[i])) {
+                        gg_options o64{};
+                        if (o) o64 = *o; else o64.device = -1;
+                        o64.precision = 1;
+                        gg_result *r32 = results[i];
+                        results[i] = nullptr;
+                        std::string msg64;
+                        if (run_chain(i, nullptr, &o64, msg64) == GG_OK && results[i]) {
+                            results[i]->reran_fp64 = true;
+                            ++g_fp64_reruns;
+                            gg_result_free(r32);
+                        } else {
+                            if (results[i]) gg_result_free(results[i]);
+                            results[i] = r32;      // keep the fp32 result, as gg_hmm_run does
+                        }
+                    }
+                    if (rc != GG_OK) record(i, rc, msg);
                 } catch (const CudaError &e) {
                     record(i, e.status, e.what());
                 } catch (const std::exception &e) {
@@ -1155,17 +1295,15 @@ int gg_hmm_run(const gg_problem *p, const gg_options *o, gg_result **out, char *
         std::fprintf(stderr, "[gg run] create %.1f ms, sweep %.1f (device %.1f), fetch %.1f, destroy %.1f, arena %llu B\n", t_create,
                      t_sweep - t_create, dev_ms, t_fetch - t_sweep, ms_since() - t_fetch, arena_b);
     if (rc != GG_OK || !was_fp32) return rc;
-    // Range guard of the fp32 path: per-column scaling keeps well-conditioned chains far from underflow, but reads
-    // that contradict each other at 1e-10 per site over many sites can push every state of a column below fp32's
-    // range (the reference computes in 80-bit long double).  A non-finite posterior triggers ONE rerun on fp64 state;
+    // Range guard of the fp32 path.  Every column's emission tables are shifted so that its best state has emission
+    // ~1 (emission_kernel) and every stored column is rescaled by its sum, which keeps chains in range whatever the
+    // reads say; this backstop remains for whatever that does not cover (the reference computes in 80-bit long
+    // double).  A non-finite posterior triggers ONE rerun on fp64 state, reported by gg_result_reran_fp64();
     // if that is non-finite too (e.g. a column whose panel alleles are all missing, where the reference itself
     // returns NaN, SURVEY B-6) the fp64 result is returned as is.
-    bool finite = true;
-    for (double v : (*out)->values)
-        if (!std::isfinite(v)) { finite = false; break; }
-    if (finite) return GG_OK;
+    if (all_finite(*out)) return GG_OK;
     gg_options o64{};
-    if (o) o64 = *o;
+    if (o) o64 = *o; else o64.device = -1;
     o64.precision = 1;
     gg_result *r64 = nullptr;
     gg_hmm *h64 = nullptr;
@@ -1176,9 +1314,13 @@ int gg_hmm_run(const gg_problem *p, const gg_options *o, gg_result **out, char *
     gg_hmm_destroy(h64);
     if (rc2 == GG_OK && r64) {
         gg_result_free(*out);
+        r64->reran_fp64 = true;
+        ++g_fp64_reruns;
         *out = r64;
     }
     return GG_OK;
 }
+
+uint64_t gg_fp64_rerun_count(void) { return g_fp64_reruns.load(); }
 
 }  // extern "C"

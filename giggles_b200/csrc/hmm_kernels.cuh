@@ -133,32 +133,75 @@ __host__ __device__ inline SmemLayout smem_layout(uint32_t R, uint32_t ngrp, uin
 
 // ---------------------------------------------------------------------------------------------
 // Emission tables: fg[b][side][slot], slot 0 = missing allele (0), slot i+1 = allele i.
+//
+// One thread per (bipartition b, side): the products over the reads on that side for every allele, in fp64
+// (reference update_emission_probability, src/genotypehmm.cpp:576-629, without its Gray-code iteration order).
+// Range (SURVEY §7 hard part 1): a column's emissions may be scaled by any positive constant (A.6), and inside a
+// block F may be traded against G.  PASS 0 finds the column's largest product m_c = max_b max F_b * max G_b
+// (emax[c], atomic max on the bit pattern of a non-negative double); PASS 1 writes F_b * 2^-eF(b) and
+// G_b * 2^(eF(b) - eM(c)) with eF = exponent of max F_b and eM = exponent of m_c.  The best state of every column
+// then has emission in [1, 4) whatever the reads say, and because the factors are powers of two the fp32 roundings
+// - hence the posteriors - are bit-identical to the unshifted tables wherever those did not underflow.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int PASS>
 __global__ void __launch_bounds__(256)
 emission_kernel(const ColDesc *__restrict__ cols, const uint8_t *__restrict__ em_side,
-                const double *__restrict__ em_prob, T *__restrict__ region, uint64_t prefix_lo, uint32_t lo) {
+                const double *__restrict__ em_prob, T *__restrict__ region, uint64_t prefix_lo, uint32_t lo,
+                double *__restrict__ emax) {
     const uint32_t c = lo + blockIdx.y;
     const ColDesc d = cols[c];
-    const uint32_t NC = d.n_alleles + 1;
-    const uint64_t n = ((uint64_t)2 * NC) << d.u;
-    T *fg = region + (d.fg_prefix - prefix_lo);
-    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t slot = (uint32_t)(idx % NC);
-        const uint64_t q = idx / NC;
-        const uint32_t side = (uint32_t)(q & 1);
-        const uint32_t b = (uint32_t)(q >> 1);
-        double p = 0.0;
-        if (slot > 0) {
-            p = 1.0;
-            const uint32_t i = slot - 1;
+    const uint32_t nA = d.n_alleles, NC = nA + 1;
+    const uint64_t n2 = (uint64_t)2 << d.u;                      // (b, side) pairs; even, so lanes 2k / 2k+1 share b
+    T *fg = PASS == 1 ? region + (d.fg_prefix - prefix_lo) : nullptr;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    int eM = 0;
+    if (PASS == 1) {
+        const double m = emax[c];
+        eM = m > 0.0 ? ilogb(m) : 0;
+    }
+    double wmax = 0.0;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n2; base += stride) {
+        const uint64_t idx = base + lane;
+        const bool active = idx < n2;
+        const uint32_t side = (uint32_t)(idx & 1), b = (uint32_t)(idx >> 1);
+        double p[GG_MAX_ALLELES];
+#pragma unroll
+        for (int i = 0; i < GG_MAX_ALLELES; ++i) p[i] = 1.0;
+        if (active)
             for (uint32_t e = 0; e < d.em_count; ++e) {
                 const uint32_t sc = em_side[d.em_off + e];
                 const uint32_t s = sc >= 64 ? sc - 64 : ((b >> sc) & 1u);
-                if (s == side) p *= em_prob[d.em_prob_off + (uint64_t)e * d.n_alleles + i];
+                if (s == side) {
+                    const double *q = em_prob + d.em_prob_off + (uint64_t)e * nA;
+#pragma unroll
+                    for (int i = 0; i < GG_MAX_ALLELES; ++i)
+                        if ((uint32_t)i < nA) p[i] *= q[i];
+                }
             }
+        double mx = 0.0;
+#pragma unroll
+        for (int i = 0; i < GG_MAX_ALLELES; ++i)
+            if ((uint32_t)i < nA) mx = fmax(mx, p[i]);
+        const double other = __shfl_xor_sync(0xffffffffu, mx, 1);
+        if (PASS == 0) {
+            if (active) wmax = fmax(wmax, mx * other);
+        } else if (active) {
+            const double mF = side == 0 ? mx : other;
+            const int eF = mF > 0.0 ? ilogb(mF) : 0;
+            const int sh = side == 0 ? -eF : eF - eM;
+            T *dst = fg + idx * NC;
+            dst[0] = T(0);
+#pragma unroll
+            for (int i = 0; i < GG_MAX_ALLELES; ++i)
+                if ((uint32_t)i < nA) dst[1 + i] = (T)ldexp(p[i], sh);
         }
-        fg[idx] = (T)p;
+    }
+    if (PASS == 0) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        if (lane == 0 && wmax > 0.0)
+            atomicMax(reinterpret_cast<unsigned long long *>(emax + c), (unsigned long long)__double_as_longlong(wmax));
     }
 }
 

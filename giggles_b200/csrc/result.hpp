@@ -6,4 +6,5 @@
 struct gg_result {
     std::vector<uint64_t> offsets;  // [C+1]
     std::vector<double> values;     // genotype posteriors, all columns back to back
+    bool reran_fp64 = false;        // the fp32 range guard replaced this chain's result by an fp64-state rerun
 };

@@ -2,6 +2,8 @@
 #include "schedule.hpp"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -11,6 +13,16 @@ namespace {
 
 constexpr uint64_t kAlign = 256;
 inline uint64_t up(uint64_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+// A planned range: a leaf, a split into parts (ends[] = last column of every part, ascending, the last one = hi), or
+// the quadratic last resort.  `cost` = bytes of backward columns produced while processing the range.
+struct Node {
+    uint32_t lo = 0, hi = 0, depth = 1;
+    enum Kind : uint8_t { LEAF, SPLIT, QUAD } kind = LEAF;
+    double cost = 0;
+    std::vector<uint32_t> ends;
+    std::vector<Node> parts;
+};
 
 struct Builder {
     const std::vector<uint64_t> &colb, &fgb;
@@ -41,7 +53,207 @@ struct Builder {
     }
     // bytes a leaf over [lo, hi] allocates: betas lo..hi-1 and the F/G tables lo..hi
     uint64_t leaf_need(uint32_t lo, uint32_t hi) const { return (pcol[hi] - pcol[lo]) + up(pfg[hi + 1] - pfg[lo]); }
+    // bytes of the two rolling backward columns and their tables while [lo, hi] is swept
+    uint64_t roll_need(uint32_t lo, uint32_t hi) const {
+        uint64_t maxcol = 0, maxfg = 0;
+        for (uint32_t c = lo; c <= hi; ++c) {
+            maxcol = std::max(maxcol, up(colb[c]));
+            maxfg = std::max(maxfg, up(fgb[c]));
+        }
+        return 2 * maxcol + 2 * maxfg;
+    }
+    double span_bytes(uint32_t lo, uint32_t hi) const { return lo > hi ? 0.0 : (double)(pcol[hi + 1] - pcol[lo]); }
 
+    // ------------------------------------------------------------------ planning (no ops emitted)
+    // smallest s >= lo such that [s, e] is a leaf within cap; false if not even [e, e] is
+    bool leaf_start(uint32_t lo, uint32_t e, uint64_t cap, uint32_t &s0) const {
+        if (leaf_need(e, e) > cap) return false;
+        uint32_t a = lo, b = e;
+        while (a < b) {
+            const uint32_t m = a + (b - a) / 2;
+            if (leaf_need(m, e) <= cap) b = m; else a = m + 1;
+        }
+        s0 = a;
+        return true;
+    }
+
+    // Two-level plan of [lo, hi]: one backward sweep that keeps checkpoints, then leaves left to right.  Part j is
+    // processed while the checkpoints of parts j..m-2 are still resident (they are released one by one), so parts grow
+    // towards the right: built right to left, every part the longest leaf that fits beside what is resident then.  A
+    // checkpoint costs every part to its left its size, so small columns are preferred as part ends: the end p of the
+    // next part maximises (columns gained) - mu * (columns still to cover) * bytes(p).
+    bool plan_two_level(uint32_t lo, uint32_t hi, uint64_t avail, double mu, uint64_t roll, std::vector<uint32_t> &ends,
+                        uint64_t *ck_bytes = nullptr) const {
+        ends.assign(1, hi);
+        uint64_t used = 0;
+        uint32_t e = hi;
+        for (;;) {
+            if (used > avail) return false;
+            uint32_t s0;
+            if (!leaf_start(lo, e, avail - used, s0)) return false;
+            if (s0 <= lo) break;
+            uint32_t best = e - 1;
+            double best_score = -1e300;
+            for (uint32_t p = e - 1;; --p) {
+                const double score = (double)(e - p) - mu * (double)(p - lo + 1) * (double)up(colb[p]);
+                if (score > best_score) { best_score = score; best = p; }
+                if (p == s0 - 1) break;
+            }
+            used += up(colb[best]);
+            if (used + roll > avail) return false;
+            ends.push_back(best);
+            e = best;
+        }
+        std::reverse(ends.begin(), ends.end());
+        if (ck_bytes) *ck_bytes = used;
+        return true;
+    }
+
+    // The sweep of a two-level plan stops at the end of the FIRST part (its columns are only ever produced by its own
+    // leaf), so the first part should be as long as the memory left beside all checkpoints allows.  Given a feasible
+    // plan, move the end p0 of the first part to the right as far as [lo, p0] stays a leaf beside the checkpoint at p0
+    // and those of a two-level plan of (p0, hi], preferring a small column for p0.
+    void anchor_first_part(uint32_t lo, uint32_t hi, uint64_t avail, double mu, uint64_t roll, std::vector<uint32_t> &ends) const {
+        if (ends.size() < 2) return;
+        auto feasible = [&](uint32_t p0, std::vector<uint32_t> &right) {
+            uint64_t kr = 0;
+            if (!plan_two_level(p0 + 1, hi, avail, mu, roll, right, &kr)) return false;
+            const uint64_t k = kr + up(colb[p0]);
+            return k + roll <= avail && leaf_need(lo, p0) + k <= avail;
+        };
+        uint32_t a = ends[0], b = hi - 1;        // a is feasible by construction
+        std::vector<uint32_t> right, best_right;
+        while (a < b) {
+            const uint32_t m = a + (b - a + 1) / 2;
+            if (feasible(m, right)) { a = m; best_right = right; } else b = m - 1;
+        }
+        if (a == ends[0]) return;
+        // a smaller column a little to the left is worth a few columns of sweep
+        uint32_t p0 = a;
+        const uint32_t back = std::min<uint32_t>((a - ends[0]) / 4, 64);
+        for (uint32_t p = a; p + back >= a && p > ends[0]; --p)
+            if (up(colb[p]) < up(colb[p0]) && (double)(a - p) * (double)up(colb[a]) < 4.0 * (double)(up(colb[p0]) - up(colb[p]))) p0 = p;
+        if (p0 != a && !feasible(p0, best_right)) { p0 = a; if (!feasible(p0, best_right)) return; }
+        if (best_right.empty() && !feasible(p0, best_right)) return;
+        ends.assign(1, p0);
+        ends.insert(ends.end(), best_right.begin(), best_right.end());
+    }
+
+    // Parts of about `len` columns, each ending at the smallest column within a quarter of `len` of the even split.
+    void even_ends(uint32_t lo, uint32_t hi, uint32_t len, std::vector<uint32_t> &ends) const {
+        ends.assign(1, hi);
+        uint32_t e = hi;
+        const uint32_t slack = std::max<uint32_t>(len / 4, 1);
+        while (e - lo + 1 > len + len / 2) {
+            const uint32_t mid = e - len;                               // nominal end of the next part to the left
+            const uint32_t a = mid > lo + slack ? mid - slack : lo, b = std::min(e - 1, mid + slack);
+            uint32_t best = b;
+            for (uint32_t p = a; p <= b; ++p)
+                if (colb[p] < colb[best] || (colb[p] == colb[best] && (p > mid ? p - mid : mid - p) < (best > mid ? best - mid : mid - best))) best = p;
+            ends.push_back(best);
+            e = best;
+        }
+        std::reverse(ends.begin(), ends.end());
+    }
+
+    bool plan(uint32_t lo, uint32_t hi, uint64_t avail, uint32_t depth, Node &out, bool shallow_only = false) const {
+        out = Node();
+        out.lo = lo; out.hi = hi; out.depth = depth;
+        if (leaf_need(lo, hi) <= avail) {
+            out.kind = Node::LEAF;
+            out.cost = span_bytes(lo, hi > lo ? hi - 1 : lo) * (hi > lo ? 1.0 : 0.0);
+            return true;
+        }
+        if (lo == hi) return false;
+        const uint64_t roll = roll_need(lo, hi);
+        const uint32_t n = hi - lo + 1;
+        const double mean_col = span_bytes(lo, hi) / n;
+        // (1) two levels, if the range is short enough for them: every column at most twice
+        {
+            const double leaf_cols = std::max(1.0, (double)avail / std::max(mean_col, 1.0));
+            for (double m : {1.0, 4.0, 0.25, 0.0}) {
+                std::vector<uint32_t> ends;
+                if (!plan_two_level(lo, hi, avail, m / (leaf_cols * mean_col), roll, ends)) continue;
+                anchor_first_part(lo, hi, avail, m / (leaf_cols * mean_col), roll, ends);
+                out.kind = Node::SPLIT;
+                // the sweep produces columns ends[0] .. hi-1, the leaves every column but their own last one
+                out.cost = (ends.size() > 1 ? span_bytes(ends[0], hi - 1) : 0.0) + span_bytes(lo, hi);
+                for (uint32_t e : ends) out.cost -= (double)up(colb[e]);
+                out.ends.swap(ends);
+                return true;                 // parts stay empty: all leaves, built by the emitter
+            }
+        }
+        // (2) more levels: parts of about n/m columns ending at small columns, each planned recursively.  The number of
+        //     parts is searched on a geometric grid from the largest the checkpoint memory allows downwards: more parts
+        //     = fewer leaves per part = a larger share of columns that the part's own sweep skips, until the part-end
+        //     checkpoints crowd out the leaves.  Plans whose parts all get by with two levels are preferred; deeper
+        //     ones are costed only when there is no such plan.
+        if (shallow_only) return false;
+        std::vector<std::vector<uint32_t>> cands;
+        for (uint32_t m = 2; m <= n / 2 && m <= (1u << 16); m = m + std::max<uint32_t>(1, m / 4)) {
+            std::vector<uint32_t> ends;
+            even_ends(lo, hi, std::max<uint32_t>(2, n / m), ends);
+            if (ends.size() < 2) continue;
+            uint64_t ck = 0;
+            for (size_t j = 0; j + 1 < ends.size(); ++j) ck += up(colb[ends[j]]);
+            if (ck + roll > avail) break;               // more parts only need more checkpoint memory
+            cands.push_back(std::move(ends));
+        }
+        bool found = false, found_shallow = false;
+        uint32_t worse_in_a_row = 0, deep_costed = 0;
+        for (size_t ci = cands.size(); ci-- > 0;) {
+            const std::vector<uint32_t> &ends = cands[ci];
+            Node cand;
+            cand.lo = lo; cand.hi = hi; cand.depth = depth; cand.kind = Node::SPLIT;
+            cand.ends = ends;
+            cand.parts.resize(ends.size());
+            cand.cost = span_bytes(ends[0], hi - 1);    // the sweep produces columns ends[0] .. hi-1
+            uint64_t resident = 0;
+            for (size_t j = 0; j + 1 < ends.size(); ++j) resident += up(colb[ends[j]]);
+            bool ok = true, deep = false;
+            uint32_t s0 = lo;
+            for (size_t j = 0; j < ends.size() && ok; ++j) {
+                Node &pn = cand.parts[j];
+                const uint64_t pav = avail - resident;
+                // once a plan whose parts get by with two levels exists, deeper parts are not worth costing
+                ok = plan(s0, ends[j], pav, depth + 1, pn, found_shallow);
+                if (ok) {
+                    cand.cost += pn.cost;
+                    if (pn.kind == Node::SPLIT && !pn.parts.empty()) deep = true;
+                    if (pn.kind == Node::QUAD) deep = true;
+                }
+                if (j + 1 < ends.size()) resident -= up(colb[ends[j]]);
+                s0 = ends[j] + 1;
+                if (found && cand.cost >= out.cost) ok = false;       // already worse than the best plan
+            }
+            if (std::getenv("GG_SCHED_TRACE") && depth <= 2)
+                std::fprintf(stderr, "[sched] depth %u [%u,%u] cand m=%zu ok=%d deep=%d cost/span=%.3f\n", depth, lo, hi, ends.size(), (int)ok, (int)deep, cand.cost / span_bytes(lo, hi));
+            if (ok && (!found || cand.cost < out.cost)) {
+                out = std::move(cand);
+                found = true;
+                found_shallow = found_shallow || !deep;
+                worse_in_a_row = 0;
+            } else if (found) {
+                if (++worse_in_a_row >= 4) break;
+            }
+            if (ok && deep && ++deep_costed >= 3) break;
+        }
+        if (found) return true;
+        // (3) last resort (columns of a fifth of HBM): two rolling columns only, the backward chain is recomputed from
+        //     the range's last column for every forward column.  Quadratic in the range length.
+        if (avail >= roll) {
+            out.kind = Node::QUAD;
+            out.ends.clear();
+            out.parts.clear();
+            double cost = 0;
+            for (uint32_t c = lo; c < hi; ++c) cost += span_bytes(c, hi - 1);
+            out.cost = cost;
+            return true;
+        }
+        return false;
+    }
+
+    // ------------------------------------------------------------------ emission
     void emit(uint32_t lo, uint32_t hi, uint64_t region) {
         Op o{};
         o.kind = OP_EMIT; o.c = lo; o.hi = hi; o.out_off = region;
@@ -53,6 +265,7 @@ struct Builder {
         o.kind = OP_BWD; o.c = c_out; o.in_off = in_off; o.out_off = out_off; o.fg_in_off = fg_in; o.fg_out_off = fg_out;
         s.ops.push_back(o);
         ++s.n_bwd;
+        s.bwd_col_bytes += colb[c_out];
     }
     void fwd(uint32_t c, uint64_t beta_off, uint64_t fg_out) {
         Op o{};
@@ -75,88 +288,43 @@ struct Builder {
         top = mark;
     }
 
-    // largest e >= s0 such that leaf_need(s0, e) <= cap (assumes leaf_need(s0, s0) <= cap)
-    uint32_t extend(uint32_t s0, uint32_t hi, uint64_t cap) const {
-        uint32_t a = s0, b = hi;
-        while (a < b) {
-            uint32_t m = a + (b - a + 1) / 2;
-            if (leaf_need(s0, m) <= cap) a = m; else b = m - 1;
-        }
-        return a;
-    }
-
-    void process(uint32_t lo, uint32_t hi, uint64_t beta_hi, uint32_t depth) {
-        max_depth = std::max(max_depth, depth);
-        const uint64_t avail = budget - top;
-        if (leaf_need(lo, hi) <= avail) {
+    void run(const Node &nd, uint64_t beta_hi) {
+        max_depth = std::max(max_depth, nd.depth);
+        const uint32_t lo = nd.lo, hi = nd.hi;
+        if (nd.kind == Node::LEAF) {
             leaf(lo, hi, beta_hi);
             return;
         }
-        if (lo == hi) throw std::runtime_error("state budget too small for this problem (one column's tables do not fit)");
         uint64_t maxcol = 0, maxfg = 0;
         for (uint32_t c = lo; c <= hi; ++c) {
             maxcol = std::max(maxcol, up(colb[c]));
             maxfg = std::max(maxfg, up(fgb[c]));
         }
-        const uint64_t roll = 2 * maxcol + 2 * maxfg;
-        const uint32_t ncols = hi - lo + 1;
-        std::vector<uint32_t> ends;   // last column of every part
-        // smallest number of parts m such that the parts are leaves beside their m-1 checkpoints
-        uint32_t m0 = (uint32_t)std::min<uint64_t>(ncols, std::max<uint64_t>(2, leaf_need(lo, hi) / std::max<uint64_t>(avail, 1)));
-        for (uint32_t m = m0; m <= ncols; ++m) {
-            const uint64_t ck = (uint64_t)(m - 1) * maxcol;
-            if (avail < ck + roll) break;
-            const uint64_t cap = avail - ck;
-            std::vector<uint32_t> e;
-            uint32_t s0 = lo;
-            bool ok = true;
-            while (s0 <= hi) {
-                if (leaf_need(s0, s0) > cap) { ok = false; break; }
-                uint32_t x = extend(s0, hi, cap);
-                e.push_back(x);
-                if (e.size() > m) { ok = false; break; }
-                s0 = x + 1;
-            }
-            if (ok) { ends.swap(e); break; }
-        }
-        if (ends.empty()) {
-            // too tight for one extra level: spend about half of what is left on checkpoints and recurse into the
-            // parts, always leaving them room for two rolling columns plus two more (a part can then split again)
-            const uint64_t M = avail > 2 * maxfg ? (avail - 2 * maxfg) / std::max<uint64_t>(maxcol, 1) : 0;
-            if (M < 5 && avail >= roll) {
-                // Room for two rolling columns only (columns of tens of GB): recompute the backward chain from the
-                // range's last column for every forward column.  Quadratic in the range length, which is a handful
-                // of columns when a single column takes a fifth of HBM.
-                max_depth = std::max(max_depth, depth + 1);   // it recomputes: never report "everything fitted"
-                const uint64_t mark = top;
-                uint64_t rbuf[2], fbuf[2];
-                rbuf[0] = alloc(maxcol); rbuf[1] = alloc(maxcol);
-                fbuf[0] = alloc(maxfg); fbuf[1] = alloc(maxfg);
-                for (uint32_t c = lo; c <= hi; ++c) {
-                    uint64_t cur = beta_hi;
-                    emit(hi, hi, fbuf[hi & 1]);
-                    for (uint32_t x = hi; x > c; --x) {
-                        emit(x - 1, x - 1, fbuf[(x - 1) & 1]);
-                        bwd(x - 1, cur, rbuf[(x - 1) & 1], fbuf[x & 1], fbuf[(x - 1) & 1]);
-                        cur = rbuf[(x - 1) & 1];
-                    }
-                    fwd(c, cur, fbuf[c & 1]);
-                }
-                top = mark;
-                return;
-            }
-            if (M < 5)
-                throw std::runtime_error("state budget too small for this problem: " + std::to_string(avail) +
-                                         " bytes left for a range whose largest column takes " + std::to_string(maxcol));
-            uint64_t nck = M / 2;
-            if (M - nck < 4) nck = M - 4;
-            uint32_t m = (uint32_t)std::min<uint64_t>(nck + 1, ncols);
-            for (uint32_t j = 1; j <= m; ++j) ends.push_back(lo + (uint32_t)((uint64_t)ncols * j / m) - 1);
-        }
-        const uint32_t m = (uint32_t)ends.size();
         const uint64_t mark = top;
+        if (nd.kind == Node::QUAD) {
+            max_depth = std::max(max_depth, nd.depth + 1);   // it recomputes: never report "everything fitted"
+            uint64_t rbuf[2], fbuf[2];
+            rbuf[0] = alloc(maxcol); rbuf[1] = alloc(maxcol);
+            fbuf[0] = alloc(maxfg); fbuf[1] = alloc(maxfg);
+            for (uint32_t c = lo; c <= hi; ++c) {
+                uint64_t cur = beta_hi;
+                emit(hi, hi, fbuf[hi & 1]);
+                for (uint32_t x = hi; x > c; --x) {
+                    emit(x - 1, x - 1, fbuf[(x - 1) & 1]);
+                    bwd(x - 1, cur, rbuf[(x - 1) & 1], fbuf[x & 1], fbuf[(x - 1) & 1]);
+                    cur = rbuf[(x - 1) & 1];
+                }
+                fwd(c, cur, fbuf[c & 1]);
+            }
+            top = mark;
+            return;
+        }
+        const std::vector<uint32_t> &ends = nd.ends;
+        const uint32_t m = (uint32_t)ends.size();
+        // checkpoints are stacked so that the one consumed first (the leftmost part's) lies on top and every part
+        // gets back the room of the parts before it
         std::vector<uint64_t> ck(m, 0);
-        for (uint32_t j = 0; j + 1 < m; ++j) ck[j] = alloc(colb[ends[j]]);
+        for (int32_t j = (int32_t)m - 2; j >= 0; --j) ck[j] = alloc(colb[ends[j]]);
         ck[m - 1] = beta_hi;
         if (m > 1) {
             const uint64_t mark2 = top;
@@ -177,7 +345,13 @@ struct Builder {
         }
         uint32_t s0 = lo;
         for (uint32_t j = 0; j < m; ++j) {
-            process(s0, ends[j], ck[j], depth + 1);
+            if (!nd.parts.empty()) {
+                run(nd.parts[j], ck[j]);
+            } else {
+                max_depth = std::max(max_depth, nd.depth + 1);
+                leaf(s0, ends[j], ck[j]);
+            }
+            if (j + 1 < m) top = ck[j];       // release this part's checkpoint
             s0 = ends[j] + 1;
         }
         top = mark;
@@ -202,7 +376,11 @@ void build_schedule(const std::vector<uint64_t> &colb, const std::vector<uint64_
     o.kind = OP_BWD_INIT; o.c = C - 1; o.out_off = beta_last; o.fg_out_off = fg_last;
     out.ops.push_back(o);
     ++out.n_bwd;
-    b.process(0, C - 1, beta_last, 1);
+    Node root;
+    if (!b.plan(0, C - 1, budget - b.top, 1, root))
+        throw std::runtime_error("state budget too small for this problem: " + std::to_string(budget - b.top) +
+                                 " bytes left for the backward columns, the largest column takes " + std::to_string(maxcol));
+    b.run(root, beta_last);
     out.arena_bytes = b.high;
     out.levels = b.max_depth;
 }

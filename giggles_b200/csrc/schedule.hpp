@@ -33,6 +33,7 @@ struct Schedule {
     uint64_t arena_bytes = 0;     // high-water mark
     uint32_t levels = 0;          // 1 = everything fitted (no recompute)
     uint64_t n_bwd = 0, n_fwd = 0, n_emit = 0;
+    uint64_t bwd_col_bytes = 0;   // bytes of the columns produced by the backward steps (recompute included)
 };
 
 // colb[c]: bytes of column c (values + side sums), fgb[c]: bytes of its F/G table.

@@ -79,7 +79,13 @@ typedef struct gg_options {
                                          reuse the retired arena of that size (gg_arena_release() makes the next call ask again) */
     int32_t precision;                /* 0 = fp32 state with per-column scaling (production); 1 = fp64 state (validation) */
     int32_t kernel_variant;           /* 0 = auto; 1 = generic step kernel only (no bulk-copy pipeline), for A/B tests */
+    uint32_t flags;                   /* GG_OPT_* */
 } gg_options;
+
+/* gg_hmm_create: the handle keeps its tables on the device but no state arena; every gg_hmm_sweep borrows ONE arena
+ * shared by all such handles of the device (their sweeps are serialised).  For many chromosomes planned and resident
+ * at once (the per-chromosome loop of giggles/cli/genotype.py:196-338) when a single chain already fills HBM. */
+#define GG_OPT_SHARED_ARENA 1u
 
 typedef struct gg_result gg_result;   /* host-side result table                 */
 typedef struct gg_hmm gg_hmm;         /* device-resident problem + schedule     */
@@ -149,6 +155,11 @@ uint32_t gg_result_n_columns(const gg_result *r);
 /* flat view: all columns back to back, offsets[c]..offsets[c+1]              */
 const double *gg_result_flat(const gg_result *r, const uint64_t **offsets);
 void gg_result_free(gg_result *r);
+/* fp32 range guard: 1 if this chain's fp32 posteriors were not finite and the result comes from the one rerun on fp64
+ * state that gg_hmm_run / gg_hmm_run_batch then do (the reference computes in 80-bit long double,
+ * src/genotypehmm.cpp:203-561); gg_fp64_rerun_count() counts such reruns process-wide. */
+int gg_result_reran_fp64(const gg_result *r);
+uint64_t gg_fp64_rerun_count(void);
 /* wraps caller-provided posteriors (e.g. gathered from other ranks) so gg_result_call can be applied to them */
 gg_result *gg_result_from_host(uint32_t n_columns, const uint64_t *offsets, const double *values);
 
@@ -216,6 +227,7 @@ int64_t gg_pyset_replay(const int64_t *ops, int64_t n, int64_t *out, int64_t cap
  *      The reference's fixed sqrt(C) schedule is src/genotypehmm.cpp:130,153-156,364-383. */
 int gg_schedule_dry_run(uint32_t n_columns, const uint64_t *col_bytes, const uint64_t *fg_bytes, uint64_t budget,
                         uint64_t *arena_bytes, uint32_t *levels, uint64_t *n_bwd, uint64_t *n_fwd,
+                        uint64_t *bwd_col_bytes /* bytes of the columns the backward steps produce, recompute included */,
                         char *err, size_t errlen);
 
 /* diagnostic: device-to-device copy bandwidth in GB/s (read + write), best of `reps` copies of `bytes` */

@@ -95,6 +95,7 @@ GenotypeHMM::GenotypeHMM(ReadSet *read_set, const std::vector<float> &recombcost
     o.state_budget_bytes = 0;
     o.precision = 0;
     o.kernel_variant = 0;
+    o.flags = 0;
     char err[512] = {0};
     const int rc = gg_hmm_run(&p, &o, &result, err, sizeof(err));
     if (rc != GG_OK) throw std::runtime_error(std::string("GenotypeHMM (giggles_b200): ") + err);

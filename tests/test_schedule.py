@@ -55,3 +55,43 @@ def test_columns_of_a_fifth_of_hbm_use_the_quadratic_fallback():
     assert r["levels"] >= 2            # a recomputing schedule never reports "everything fitted"
     with pytest.raises(capi.GGError):
         capi.schedule_dry_run([col] * 8, [fg] * 8, 140_000_000_000)
+
+
+def test_full_length_config2_recompute_bound():
+    # configs[1] at its real length: 516k columns of the synthetic 30x / max-coverage-15 profile (69 % of the columns
+    # at 2^15 blocks, 1.04 GB) in a 178.5 GB state arena.  With ~170 column-sized slots no schedule gets below
+    # 3 - C(173,2)/516000 = 2.97 backward columns per column if every checkpoint costs a full column (revolve bound);
+    # choosing small columns as checkpoints and anchoring the first leaf of every part brings it to ~2.76
+    # (round 1: 3.34).  The bound asserted here is what bench.py's full-length block relies on.
+    from giggles_b200 import fullscale as fs
+    u = fs.coverage_profile(516000)
+    cb, fb = fs.column_bytes(u, 88)
+    c = fs.schedule_cost(cb, fb, int(178.5e9))
+    assert c["n_fwd"] == 516000 and c["arena_bytes"] <= int(178.5e9)
+    assert c["bwd_per_column"] <= 2.8 and c["bwd_bytes_ratio"] <= 2.8
+    assert c["levels"] == 3
+    # shorter chains: two levels suffice up to ~50k columns and a 256-column window pays ~1.1
+    for n, bound in ((256, 1.2), (2048, 1.95), (16384, 2.0), (131072, 2.5)):
+        c = fs.schedule_cost(cb[:n], fb[:n], int(178.5e9))
+        assert c["bwd_per_column"] <= bound, (n, c)
+
+
+def test_budget_matching_the_full_length_recompute():
+    from giggles_b200 import fullscale as fs
+    u = fs.coverage_profile(256)
+    cb, fb = fs.column_bytes(u, 88)
+    budget, c = fs.budget_for_ratio(cb, fb, 2.76, int(178.5e9))
+    assert 2.76 <= c["bwd_bytes_ratio"] < 2.95 and budget < int(40e9)
+    # a target nothing reaches from above falls back to the closest schedule below it
+    budget, c = fs.budget_for_ratio(cb[:4], fb[:4], 50.0, int(178.5e9))
+    assert c["n_fwd"] == 4
+
+
+def test_checkpoints_prefer_small_columns_and_parts_free_their_checkpoints():
+    # 200 columns, every 10th one 16x smaller: with room for ~12 large columns a two-level plan exists only if the
+    # checkpoints sit on the small columns and each part gets back the room of the parts before it
+    cb = np.full(200, 16 << 20, dtype=np.uint64)
+    cb[5::10] = 1 << 20
+    fb = np.full(200, 4096, dtype=np.uint64)
+    r = capi.schedule_dry_run(cb, fb, 16 * (16 << 20))
+    assert r["levels"] == 2 and r["n_bwd"] <= 2 * 200
