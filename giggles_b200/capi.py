@@ -103,7 +103,7 @@ SYMBOLS = [
     "gg_plan_build", "gg_plan_n_columns", "gg_plan_active", "gg_plan_untagged", "gg_plan_shared_mask_prev",
     "gg_plan_compatible_prev", "gg_plan_free",
     "gg_entry_emission", "gg_entry_emission_batch", "gg_transition_scalars", "gg_binomial_coefficient",
-    "gg_schedule_dry_run", "gg_version", "gg_device_count", "gg_device_copy_gbs",
+    "gg_schedule_dry_run", "gg_default_state_budget", "gg_version", "gg_device_count", "gg_device_copy_gbs",
     "gg_readselection", "gg_pyset_replay",
 ]
 
@@ -170,6 +170,8 @@ def lib() -> C.CDLL:
     L.gg_binomial_coefficient.restype = i32
     L.gg_schedule_dry_run.argtypes = [u32, C.POINTER(u64), C.POINTER(u64), u64, C.POINTER(u64), C.POINTER(u32),
                                       C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)] + errargs
+    L.gg_default_state_budget.argtypes = [C.c_int]
+    L.gg_default_state_budget.restype = u64
     L.gg_device_copy_gbs.argtypes = [C.c_int, u64, C.c_int]
     L.gg_device_copy_gbs.restype = dbl
     L.gg_version.restype = C.c_char_p

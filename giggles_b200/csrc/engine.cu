@@ -699,6 +699,11 @@ struct Engine {
             cd.em_off = cp.em_off;
             cd.em_prob_off = cp.em_prob_off;
             cd.fg_prefix = h->fg_prefix_elems[c];
+            uint32_t present = 0;
+            const uint8_t *al = pl.allele1.data() + (size_t)c * R;
+            for (uint32_t hh = 0; hh < R; ++hh)
+                if (al[hh]) present |= 1u << (al[hh] - 1);
+            cd.present = present;
         }
         // if everything fits there is no reason to reserve more than that
         uint64_t all = 0, maxcol = 0;
@@ -935,6 +940,17 @@ static uint64_t default_budget(const gg_options *o, int device) {
         g_last_queried_budget[device] = budget;
     }
     return budget;
+}
+
+uint64_t gg_default_state_budget(int device) {
+    try {
+        if (device >= 0) GG_CUDA(cudaSetDevice(device));
+        int dev = 0;
+        GG_CUDA(cudaGetDevice(&dev));
+        return default_budget(nullptr, dev);
+    } catch (const std::exception &) {
+        return 0;
+    }
 }
 
 static void hmm_schedule(gg_hmm *h, uint64_t budget);

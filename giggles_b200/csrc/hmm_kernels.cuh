@@ -43,7 +43,7 @@ constexpr int kMaxClasses = GG_MAX_ALLELES + 1;           // allele classes incl
 constexpr int kPartialStride = kMaxClasses * kMaxClasses + 3;  // W[i][j], column sum, spare
 
 struct ColDesc {              // device copy of the per-column plan (emission kernel only)
-    uint32_t u, n_alleles, em_count, pad;
+    uint32_t u, n_alleles, em_count, present;   // present: bit i set = allele i occurs in the panel at this column
     uint64_t em_off, em_prob_off;
     uint64_t fg_prefix;       // prefix sum (elements) of the F/G table sizes
 };
@@ -179,10 +179,11 @@ emission_kernel(const ColDesc *__restrict__ cols, const uint8_t *__restrict__ em
                         if ((uint32_t)i < nA) p[i] *= q[i];
                 }
             }
+        // only alleles some panel haplotype carries here can be the allele of a state (the others never reach the sweep)
         double mx = 0.0;
 #pragma unroll
         for (int i = 0; i < GG_MAX_ALLELES; ++i)
-            if ((uint32_t)i < nA) mx = fmax(mx, p[i]);
+            if ((uint32_t)i < nA && ((d.present >> i) & 1u)) mx = fmax(mx, p[i]);
         const double other = __shfl_xor_sync(0xffffffffu, mx, 1);
         if (PASS == 0) {
             if (active) wmax = fmax(wmax, mx * other);

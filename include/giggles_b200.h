@@ -230,6 +230,10 @@ int gg_schedule_dry_run(uint32_t n_columns, const uint64_t *col_bytes, const uin
                         uint64_t *bwd_col_bytes /* bytes of the columns the backward steps produce, recompute included */,
                         char *err, size_t errlen);
 
+/* the state budget gg_hmm_create uses on `device` when gg_options.state_budget_bytes is 0 (94 % of the free memory,
+ * arenas retired by earlier handles counted as free); 0 without a device */
+uint64_t gg_default_state_budget(int device);
+
 /* diagnostic: device-to-device copy bandwidth in GB/s (read + write), best of `reps` copies of `bytes` */
 double gg_device_copy_gbs(int device, uint64_t bytes, int reps);
 

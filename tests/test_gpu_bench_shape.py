@@ -1,0 +1,83 @@
+"""Parity AT THE BENCH SHAPE: the pipelined step kernel with many work items per CTA, checked against the CPU
+oracle (not against another mode of the same engine).
+
+The grid of `step_tma_kernel` is min(2^u, 296) persistent CTAs, so only columns with u >= 10 make a CTA walk several
+items: ring wrap-around and parity flips across items, the one-item-ahead F/G prefetch, the L2 look-ahead of the
+forward step (needs `far < n_items`), the double-buffered column-sum scratch.  The oracle is O(states) per column
+(about 12 M states/s on one core), so these problems are a handful of columns each.  Reference functions under test:
+src/genotypehmm.cpp:249-323 (backward), :412-509 (forward), src/column.cpp:72-122 (compatible bipartitions).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import assert_posteriors_close
+from giggles_b200 import capi
+from giggles_b200.synth import make_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _need_device(have_gpu):
+    if not have_gpu:
+        pytest.fail("no CUDA device: the GenotypeHMM path has no CPU fallback")
+
+
+# (name, make_problem kwargs, minimum max-u the problem must reach, kernel variants)
+SHAPES = [
+    # short reads: several reads start and end inside the window (reduce sets of 2 and 4 blocks, broadcast bits)
+    ("R88_u11_events", dict(n_columns=8, n_haps=88, region_bp=8 * 124, coverage=40, max_coverage=11, read_len_mean=500,
+                            read_len_sigma=0.5, window=True, seed=1101), 10, (0, 2, 3)),
+    # long reads: block-local steps, 14 items per CTA, look-ahead live in every launch
+    ("R88_u12_window", dict(n_columns=5, n_haps=88, region_bp=5 * 124, coverage=30, max_coverage=12, window=True,
+                            seed=1102), 12, (0,)),
+    ("R88_u10_mixed_tags_multiallelic", dict(n_columns=8, n_haps=88, region_bp=8 * 124, coverage=60, max_coverage=20,
+                                             read_len_mean=600, read_len_sigma=0.5, tags="mixed", window=True,
+                                             multiallelic_frac=0.4, max_alleles=6, missing_frac=0.02, seed=1103), 9, (0, 3)),
+    ("R94_u10_events", dict(n_columns=8, n_haps=94, region_bp=8 * 124, coverage=40, max_coverage=10, read_len_mean=500,
+                            read_len_sigma=0.5, window=True, seed=1104), 9, (0, 2)),       # float2 rows (R % 4 == 2)
+    ("R128_u10_events", dict(n_columns=6, n_haps=128, region_bp=6 * 124, coverage=40, max_coverage=10, read_len_mean=400,
+                             read_len_sigma=0.5, window=True, seed=1105), 9, (0, 2)),
+]
+
+
+@pytest.mark.parametrize("name,kw,min_u,variants", SHAPES, ids=[s[0] for s in SHAPES])
+def test_many_items_per_cta_against_oracle(name, kw, min_u, variants):
+    p = make_problem(**kw)
+    u = p.untagged_per_column()
+    assert int(u.max()) >= min_u, u.tolist()          # 2^u >> 296 CTAs
+    want = oracle.oracle_run(p)
+    assert np.isfinite(want).all()
+    for kv in variants:
+        got = capi.hmm_run(p, device=0, kernel_variant=kv).values
+        assert_posteriors_close(got, want)
+    # a tight budget forces recompute launches at this size too; results must not move by a bit
+    base = capi.hmm_run(p, device=0).values
+    h = capi.Hmm(p, device=0)
+    full = h.stats()["state_bytes_reserved"]
+    h.close()
+    for frac in (0.5, 0.7):
+        try:
+            h = capi.Hmm(p, device=0, budget=int(full * frac))
+        except capi.GGError as e:
+            assert e.status == capi.GG_ERR_NOMEM
+            continue
+        h.sweep()
+        assert np.array_equal(h.fetch().values, base)
+        h.close()
+        break
+
+
+def test_u_changes_inside_the_window_really_happen():
+    # guard for the cases above: the "events" shapes must contain reads that start and reads that end inside
+    p = make_problem(**SHAPES[0][1])
+    u = p.untagged_per_column()
+    assert len(set(u.tolist())) >= 2
+    pv = capi.PlanView(p)
+    started = ended = 0
+    for c in range(1, p.n_columns):
+        a, b = set(pv.untagged(c - 1)), set(pv.untagged(c))
+        started += len(b - a)
+        ended += len(a - b)
+    assert started >= 2 and ended >= 2

@@ -121,25 +121,34 @@ def test_all_tagged_chain_matches_per_column_kernels():
     assert_posteriors_close(capi.hmm_run(p, device=0, kernel_variant=4).values, want)
 
 
-def test_fp32_underflow_falls_back_to_fp64_state():
-    # five reads that all contradict the panel at 1e-10 each: every state of column 0 has emission 1e-50, below fp32
-    # range; the reference (80-bit) still gets the answer.  gg_hmm_run notices the non-finite fp32 result and reruns
-    # on fp64 state; the staged API (no guard) shows what the fp32 path alone produces.
+def _underflow_problem(n=5, second=-1.0):
+    # n reads that all contradict the panel at 1e-13 each: every state of column 0 has emission 1e-65, far below
+    # fp32 range; the reference (80-bit) still gets the answer
     from giggles_b200.problem import Problem
-    n = 5
-    p = Problem(positions=[100, 200], n_alleles=[2, 2], allele_ref=[[1, 1, 1, 1], [0, 1, 0, 1]], recomb=[0.01],
-                read_tag=[-1] * n, read_entry_offset=np.arange(0, 2 * n + 1, 2), entry_column=[0, 1] * n,
-                entry_allele=[0, 0] * n, entry_score_offset=np.arange(0, 4 * n + 1, 2),
-                entry_scores=[0.0, -30.0, 0.0, -1.0] * n)
-    want = oracle.oracle_run(p)
-    assert np.isfinite(want).all()
-    h = capi.Hmm(p, device=0)
-    h.sweep()
-    raw32 = h.fetch().values
-    h.close()
-    assert not np.isfinite(raw32).all()
-    got = capi.hmm_run(p, device=0).values
-    assert np.abs(got - want).max() <= 1e-11
+    return Problem(positions=[100, 200], n_alleles=[2, 2], allele_ref=[[1, 1, 1, 1], [0, 1, 0, 1]], recomb=[0.01],
+                   read_tag=[-1] * n, read_entry_offset=np.arange(0, 2 * n + 1, 2), entry_column=[0, 1] * n,
+                   entry_allele=[0, 0] * n, entry_score_offset=np.arange(0, 4 * n + 1, 2),
+                   entry_scores=[0.0, -30.0, 0.0, second] * n)
+
+
+def test_fp32_stays_in_range_when_every_state_underflows():
+    # the per-column emission shift (emission_kernel: best state of every column ~1, exact powers of two) keeps the
+    # fp32 path in range on its own: no fp64 rerun, tolerance of the fp32 path
+    before = capi.lib().gg_fp64_rerun_count()
+    for p in (_underflow_problem(), _underflow_problem(12, -30.0)):
+        want = oracle.oracle_run(p)
+        assert np.isfinite(want).all()
+        h = capi.Hmm(p, device=0)              # the staged API has no guard at all
+        h.sweep()
+        raw32 = h.fetch().values
+        h.close()
+        assert np.isfinite(raw32).all()
+        assert_posteriors_close(raw32, want)
+        r = capi.hmm_run(p, device=0)
+        assert not r.reran_fp64 and np.array_equal(r.values, raw32)
+        rb = capi.hmm_run_batch([p, p], device=0)
+        assert all(not x.reran_fp64 and np.array_equal(x.values, raw32) for x in rb)
+    assert capi.lib().gg_fp64_rerun_count() == before
 
 
 def test_batch_of_chains_matches_single_runs():

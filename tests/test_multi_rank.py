@@ -33,7 +33,8 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    probs = [make_problem(10 + 3 * i, 4 + i % 3, coverage=4, max_coverage=4, read_len_mean=1500, seed=70 + i,
+    # uneven shares: chains of very different lengths and allele counts (exact-size send / recv, no padding)
+    probs = [make_problem([40, 6, 9, 25, 3][i], 4 + i % 3, coverage=4, max_coverage=4, read_len_mean=1500, seed=70 + i,
                           multiallelic_frac=0.3, max_alleles=4) for i in range(5)]
     out = run_sharded(probs, oracle.oracle_run, rank, world, dist=dist)
     dist.barrier()
@@ -41,6 +42,21 @@ def _worker(rank, world, port, q):
         ok = all(np.array_equal(out[i], oracle.oracle_run(probs[i])) for i in range(len(probs)))
         q.put(ok)
     dist.destroy_process_group()
+
+
+def test_torch_free_gather_through_result_files(tmp_path):
+    # dist=None with world_size 2: every rank leaves its share in result_dir, collect_result_dir assembles them
+    sys.path.insert(0, ROOT)
+    import oracle
+    from giggles_b200.shard import collect_result_dir, run_sharded
+    from giggles_b200.synth import make_problem
+    probs = [make_problem(8 + 2 * i, 4, coverage=3, max_coverage=3, read_len_mean=1500, seed=90 + i) for i in range(5)]
+    for r in range(2):
+        assert run_sharded(probs, oracle.oracle_run, r, 2, result_dir=str(tmp_path)) is None
+    out = collect_result_dir(probs, 2, str(tmp_path))
+    assert all(np.array_equal(out[i], oracle.oracle_run(probs[i])) for i in range(5))
+    with pytest.raises(ValueError):
+        run_sharded(probs, oracle.oracle_run, 0, 2)
 
 
 def test_two_ranks_gloo_gather():

@@ -83,3 +83,14 @@ def test_unsorted_reads_are_rejected_like_the_reference():
     with pytest.raises(capi.GGError, match="not sorted") as ei:
         capi.PlanView(q)
     assert ei.value.status == capi.GG_ERR_INVALID
+
+
+@needs_ref
+def test_planner_matches_reference_up_to_13_bits():
+    # the masks the kernels decode with (shared / terminating bits, src/column.cpp:72-122) at bipartition counts where
+    # a CTA of the pipelined kernel walks many items: every b of every column against the reference's own lists
+    p = make_problem(14, 4, region_bp=14 * 124, coverage=30, max_coverage=13, read_len_mean=500, read_len_sigma=0.5,
+                     window=True, seed=1203)
+    u = p.untagged_per_column()
+    assert int(u.max()) >= 12 and len(set(u.tolist())) >= 3
+    _check_against_reference(p, max_bits=13)
