@@ -328,6 +328,15 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
+    # the same K steps without the per-launch events (what the instrumentation costs; matters for the side workloads
+    # whose kernels last microseconds)
+    barrier()
+    t0p = time.perf_counter()
+    for _ in range(args.steps):
+        for i in mine:
+            hs[i].sweep()
+    barrier()
+    plain_wall = time.perf_counter() - t0p
     res_dev = {i: hs[i].fetch().values for i in mine}
     for i in mine:
         hs[i].close()
@@ -382,15 +391,15 @@ def main():
         allr = [torch.empty_like(mine_t) for _ in range(world)]
         dist.all_gather(allr, mine_t)
         per_rank = [[round(float(x), 1) for x in r.tolist()] for r in allr]
-        t = torch.tensor([dev_ms, wall * 1e3, e2e_wall * 1e3], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, wall * 1e3, e2e_wall * 1e3, plain_wall * 1e3], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms_max, wall_ms, e2e_ms = [float(x) for x in t.tolist()]
+        dev_ms_max, wall_ms, e2e_ms, plain_ms = [float(x) for x in t.tolist()]
         tot = torch.tensor([fwd_ms, bwd_ms, fwd_bytes, bwd_bytes, float(n_fwd), float(n_bwd), float(launches), float(h2d), float(d2h),
                             sched_bytes], dtype=torch.float64, device="cuda")
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         fwd_ms, bwd_ms, fwd_bytes, bwd_bytes, n_fwd, n_bwd, launches, h2d, d2h, sched_bytes = [float(x) for x in tot.tolist()]
     else:
-        wall_ms, e2e_ms, dev_ms_max = wall * 1e3, e2e_wall * 1e3, dev_ms
+        wall_ms, e2e_ms, dev_ms_max, plain_ms = wall * 1e3, e2e_wall * 1e3, dev_ms, plain_wall * 1e3
         per_rank = None
     if rank != 0:
         dist.destroy_process_group()
@@ -452,6 +461,7 @@ def main():
         "data": "synthetic", "config": config,
         "hmm_columns_per_s": value, "state_columns_per_s": total_states * args.steps / (wall_ms / 1e3),
         "device_ms_per_step": dev_ms_max / args.steps,
+        "value_without_launch_events": total_cols * args.steps / (plain_ms / 1e3),
         "value_note": "timed region = K steps of gg_hmm_sweep over resident chains with a CUDA event pair around every launch "
                       "(the per-kernel times of `roofline` come from the same region; costs ~1 %)",
         "roofline": roofline,

@@ -107,6 +107,18 @@ __device__ __forceinline__ uint32_t dev_pdep(uint32_t x, uint32_t mask) {
     return r;
 }
 
+// Last-CTA reduction: fixed-order sum of one slot over the per-CTA partial records, by ONE WARP (lane l takes records
+// l, l+32, ... in fp64, then a butterfly).  The order depends on the grid size only, so results stay bit-reproducible;
+// a single thread walking all records serially cost several microseconds per launch (every load an L2 round trip).
+template <typename T>
+__device__ __forceinline__ double warp_sum_partials(const T *partial, uint32_t nblk, uint32_t slot, uint32_t lane) {
+    double acc = 0.0;
+    for (uint32_t blk = lane; blk < nblk; blk += 32) acc += (double)__ldcg(partial + (uint64_t)blk * kPartialStride + slot);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
+}
+
 // Shared-memory carve-up, identical on host (size) and device (pointers).
 struct SmemLayout {
     uint32_t off_rowv, off_colv, off_fo, off_fi, off_colred, off_totred, off_q, off_al_o, off_al_i, off_rord, total;
@@ -515,11 +527,10 @@ step_kernel(const StepArgs<T> a) {
     if (!s_last) return;
     __threadfence();
     const uint32_t npair = FWD ? NCo * NCo : 0u;
-    for (uint32_t p = tid; p < npair + 1; p += blockDim.x) {
+    for (uint32_t p = warp; p < npair + 1; p += nwarps) {
         const uint32_t slot = (p == npair) ? (uint32_t)(kMaxClasses * kMaxClasses) : p;
-        double acc = 0.0;
-        for (uint32_t blk = 0; blk < gridDim.x; ++blk) acc += (double)__ldcg(a.partial + (uint64_t)blk * kPartialStride + slot);
-        s_W[slot] = acc;
+        const double acc = warp_sum_partials(a.partial, gridDim.x, slot, lane);
+        if (lane == 0) s_W[slot] = acc;
     }
     __syncthreads();
     if (tid == 0) {

@@ -682,11 +682,10 @@ step_tma_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_t
     double *s_W = reinterpret_cast<double *>(smem_raw + L.off_stage);
     double *s_L = s_W + kPartialStride;
     const uint32_t npair = FWD ? NCo * NCo : 0u;
-    for (uint32_t p = ctid; p < npair + 1; p += nct) {
+    for (uint32_t p = cwarp; p < npair + 1; p += CW) {
         const uint32_t slot = (p == npair) ? (uint32_t)(kMaxClasses * kMaxClasses) : p;
-        double acc = 0.0;
-        for (uint32_t blk = 0; blk < gridDim.x; ++blk) acc += (double)__ldcg(a.partial + (uint64_t)blk * kPartialStride + slot);
-        s_W[slot] = acc;
+        const double acc = warp_sum_partials(a.partial, gridDim.x, slot, lane);
+        if (lane == 0) s_W[slot] = acc;
     }
     consumer_bar(nct);
     if (ctid == 0) {

@@ -288,11 +288,10 @@ step_warp_kernel(const StepArgs<float> a) {
     if (!s_last) return;
     __threadfence();
     const uint32_t npair = FWD ? NCo * NCo : 0u;
-    for (uint32_t p = tid; p < npair + 1; p += blockDim.x) {
+    for (uint32_t p = warp; p < npair + 1; p += kWarpKernelWarps) {
         const uint32_t slot = (p == npair) ? (uint32_t)(kMaxClasses * kMaxClasses) : p;
-        double acc = 0.0;
-        for (uint32_t blk = 0; blk < gridDim.x; ++blk) acc += (double)__ldcg(a.partial + (uint64_t)blk * kPartialStride + slot);
-        s_W[slot] = acc;
+        const double acc = warp_sum_partials(a.partial, gridDim.x, slot, lane);
+        if (lane == 0) s_W[slot] = acc;
     }
     __syncthreads();
     if (tid == 0) {

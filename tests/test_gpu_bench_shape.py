@@ -24,21 +24,26 @@ def _need_device(have_gpu):
         pytest.fail("no CUDA device: the GenotypeHMM path has no CPU fallback")
 
 
+# Weak evidence per read (emission ratio 1.1 per unit of edit distance instead of e, 80 % of the entries support the
+# true allele): with ten or more reads per column the default scores saturate every posterior at 0 or 1 and a wrong
+# block among thousands would go unnoticed; these leave most columns with posteriors well inside (0, 1).
+SOFT = dict(base_const=1.1, accuracy=0.8)
+
 # (name, make_problem kwargs, minimum max-u the problem must reach, kernel variants)
 SHAPES = [
     # short reads: several reads start and end inside the window (reduce sets of 2 and 4 blocks, broadcast bits)
     ("R88_u11_events", dict(n_columns=8, n_haps=88, region_bp=8 * 124, coverage=40, max_coverage=11, read_len_mean=500,
-                            read_len_sigma=0.5, window=True, seed=1101), 10, (0, 2, 3)),
+                            read_len_sigma=0.5, window=True, seed=1101, **SOFT), 10, (0, 2, 3)),
     # long reads: block-local steps, 14 items per CTA, look-ahead live in every launch
     ("R88_u12_window", dict(n_columns=5, n_haps=88, region_bp=5 * 124, coverage=30, max_coverage=12, window=True,
-                            seed=1102), 12, (0,)),
+                            seed=1102, **SOFT), 12, (0,)),
     ("R88_u10_mixed_tags_multiallelic", dict(n_columns=8, n_haps=88, region_bp=8 * 124, coverage=60, max_coverage=20,
                                              read_len_mean=600, read_len_sigma=0.5, tags="mixed", window=True,
-                                             multiallelic_frac=0.4, max_alleles=6, missing_frac=0.02, seed=1103), 9, (0, 3)),
+                                             multiallelic_frac=0.4, max_alleles=6, missing_frac=0.02, seed=1103, **SOFT), 9, (0, 3)),
     ("R94_u10_events", dict(n_columns=8, n_haps=94, region_bp=8 * 124, coverage=40, max_coverage=10, read_len_mean=500,
-                            read_len_sigma=0.5, window=True, seed=1104), 9, (0, 2)),       # float2 rows (R % 4 == 2)
+                            read_len_sigma=0.5, window=True, seed=1104, **SOFT), 9, (0, 2)),       # float2 rows (R % 4 == 2)
     ("R128_u10_events", dict(n_columns=6, n_haps=128, region_bp=6 * 124, coverage=40, max_coverage=10, read_len_mean=400,
-                             read_len_sigma=0.5, window=True, seed=1105), 9, (0, 2)),
+                             read_len_sigma=0.5, window=True, seed=1105, **SOFT), 9, (0, 2)),
 ]
 
 
@@ -49,6 +54,7 @@ def test_many_items_per_cta_against_oracle(name, kw, min_u, variants):
     assert int(u.max()) >= min_u, u.tolist()          # 2^u >> 296 CTAs
     want = oracle.oracle_run(p)
     assert np.isfinite(want).all()
+    assert np.mean((want > 1e-4) & (want < 0.999)) > 0.3          # not saturated: the comparison discriminates
     for kv in variants:
         got = capi.hmm_run(p, device=0, kernel_variant=kv).values
         assert_posteriors_close(got, want)

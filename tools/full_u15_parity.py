@@ -17,7 +17,7 @@ from giggles_b200.synth import make_problem  # noqa: E402
 
 seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1511
 p = make_problem(5, 88, region_bp=5 * 124, coverage=40, max_coverage=15, read_len_mean=5000, read_len_sigma=0.6,
-                 window=True, seed=seed)
+                 window=True, seed=seed, base_const=1.1, accuracy=0.8)    # weak evidence: unsaturated posteriors
 u = p.untagged_per_column().tolist()
 pv = capi.PlanView(p)
 started = ended = 0
@@ -33,5 +33,6 @@ big = want >= 1e-3
 for kv, g in got.items():
     out[f"variant{kv}_max_rel_err_p_ge_1e-3"] = float(np.max(np.abs(g[big] - want[big]) / want[big]))
     out[f"variant{kv}_max_abs_err_p_lt_1e-3"] = float(np.max(np.abs(g[~big] - want[~big]))) if (~big).any() else 0.0
+out["posteriors_strictly_inside_1e-4_0.999"] = float(np.mean((want > 1e-4) & (want < 0.999)))
 out["pass"] = all(out[f"variant{kv}_max_rel_err_p_ge_1e-3"] <= 1e-5 and out[f"variant{kv}_max_abs_err_p_lt_1e-3"] <= 2e-6 for kv in got)
 print(json.dumps(out))
