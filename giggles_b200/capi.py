@@ -104,7 +104,7 @@ SYMBOLS = [
     "gg_plan_compatible_prev", "gg_plan_free",
     "gg_entry_emission", "gg_entry_emission_batch", "gg_transition_scalars", "gg_binomial_coefficient",
     "gg_schedule_dry_run", "gg_default_state_budget", "gg_version", "gg_device_count", "gg_device_copy_gbs",
-    "gg_readselection", "gg_pyset_replay",
+    "gg_readselection", "gg_pyset_replay", "gg_edit_distance_batch",
 ]
 
 _lib = None
@@ -158,6 +158,8 @@ def lib() -> C.CDLL:
     L.gg_plan_free.restype = None
     L.gg_readselection.argtypes = [C.POINTER(gg_readset_view), u32, C.POINTER(i32), u32, C.c_int, C.POINTER(u32),
                                    C.POINTER(u32)] + errargs
+    L.gg_edit_distance_batch.argtypes = [C.POINTER(C.c_uint8), u64, C.POINTER(u64), C.POINTER(u32), C.POINTER(u64), C.POINTER(u32),
+                                         C.POINTER(i32), u32, C.POINTER(i32), i32] + errargs
     L.gg_pyset_replay.argtypes = [C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64), C.c_int64]
     L.gg_pyset_replay.restype = C.c_int64
     L.gg_entry_emission.argtypes = [C.POINTER(dbl), u32, i32, dbl, C.POINTER(dbl)]

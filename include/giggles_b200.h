@@ -222,6 +222,17 @@ int gg_readselection(const gg_readset_view *rs, uint32_t max_cov, const int32_t 
 /* test hook: replays a script of Python-set operations on the order-exact set model (readselect.cpp) */
 int64_t gg_pyset_replay(const int64_t *ops, int64_t n, int64_t *out, int64_t cap);
 
+/* ---- batched edit distance: edit_distance(s, t, maxdiff) of giggles/align.pyx:15-107 for n_pairs pairs
+ *      at once, on the device.  This is the aligner of the allele detection by realignment in "edit" mode
+ *      (giggles/variants.py:50-51,238-239: one call per read x variant x allele, maxdiff = -1).  Pair i compares
+ *      pool[s_off[i] .. +s_len[i]) with pool[t_off[i] .. +t_len[i]) (byte strings; the same query may be shared by
+ *      several pairs).  maxdiff == NULL or maxdiff[i] == -1: the edit distance.  maxdiff[i] >= 0: the reference's banded
+ *      result, bit for bit (the true distance iff it is <= maxdiff, otherwise whatever value > maxdiff the reference's
+ *      band bookkeeping yields; abs(len difference) when that already exceeds maxdiff).  H2D / D2H copies inside. */
+int gg_edit_distance_batch(const uint8_t *pool, uint64_t pool_bytes, const uint64_t *s_off, const uint32_t *s_len,
+                           const uint64_t *t_off, const uint32_t *t_len, const int32_t *maxdiff, uint32_t n_pairs,
+                           int32_t *out, int32_t device, char *err, size_t errlen);
+
 /* ---- checkpoint schedule dry run (host only, no device): builds and self-checks the launch
  *      schedule gg_hmm_create would use for columns of the given byte sizes under `budget`.
  *      The reference's fixed sqrt(C) schedule is src/genotypehmm.cpp:130,153-156,364-383. */

@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE — loaders for the CPU oracle (oracle/hmm_oracle.c) and for the compiled
+"""TEST INFRASTRUCTURE — loaders for the CPU oracle (oracle/hmm_oracle.c, oracle/edit_oracle.c) and for the compiled
 reference (oracle/_ref/libgiggles_ref.so, built by oracle/build_ref.sh from the reference's own
 sources).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
 may import this package; the product (giggles_b200/) never does.
@@ -57,6 +57,32 @@ def oracle_run(p) -> np.ndarray:
     if rc != 0:
         raise RuntimeError(f"oracle_hmm_run failed ({rc})")
     return out
+
+
+def oracle_edit_distance(s, t, maxdiff: int = -1) -> int:
+    """C restatement of the reference's edit_distance (oracle/edit_oracle.c, follows giggles/align.pyx:15-107)."""
+    # align.pyx:30-31,42-45: lengths are taken from the str (characters), the comparison runs over the UTF-8 bytes:
+    # for non-ASCII text the reference looks at the first len(s) BYTES only
+    sb = s.encode()[:len(s)] if isinstance(s, str) else bytes(s)
+    tb = t.encode()[:len(t)] if isinstance(t, str) else bytes(t)
+    L = oracle_lib()
+    L.oracle_edit_distance.restype = C.c_int
+    return int(L.oracle_edit_distance(sb, len(sb), tb, len(tb), int(maxdiff)))
+
+
+def reference_edit_distance():
+    """The reference's own Cython edit_distance (oracle/_ref/pyref, built by build_ref.sh --python) or None."""
+    import importlib
+    import sys
+    if not os.path.isdir(os.path.join(PYREF, "giggles")):
+        return None
+    sys.path.insert(0, PYREF)
+    try:
+        return importlib.import_module("giggles.align").edit_distance
+    except Exception:
+        return None
+    finally:
+        sys.path.remove(PYREF)
 
 
 def oracle_entry_emission(scores, reg_const=10, base_const=float(np.e)) -> np.ndarray:

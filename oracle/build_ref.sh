@@ -6,8 +6,8 @@
 # reference's build system is not run and no reference source is copied into
 # this repository.  Outputs (git-ignored, but shipped to the GPU box):
 #   oracle/_ref/libgiggles_ref.so   reference core + oracle/ref_driver.cpp (C entry points)
-#   oracle/_ref/pyref/giggles/      (optional, --python) the reference's Cython module
-#                                   giggles.core, for generating tests/golden fixtures
+#   oracle/_ref/pyref/giggles/      (optional, --python) the reference's Cython modules giggles.core and
+#                                   giggles.align, for generating tests/golden fixtures
 # Flags follow SURVEY Appendix C: -std=c++11 (std::bind2nd), -include cstdint
 # (GCC 13 needs it for genotype.h:54), asserts live (-UNDEBUG) like setup.py:14.
 set -euo pipefail
@@ -52,7 +52,11 @@ if [[ $WITH_PY == 1 ]]; then
     g++ -std=c++11 -O2 -fPIC -w -I"$PYINC" -I"$W/giggles" -c "$W/pq.cpp" -o "$W/pq.o"
     g++ -shared -o "$W/giggles/priorityqueue$EXT" "$W/pq.o"
     rm -rf "$OUT/pyref"; mkdir -p "$OUT/pyref/giggles"
-    cp "$W/giggles/core$EXT" "$W/giggles/priorityqueue$EXT" "$OUT/pyref/giggles/"
+    # edit_distance (giggles/align.pyx): plain C Cython module, the pin of the batched device edit distance
+    (cd "$W" && cython -3 giggles/align.pyx -o "$W/align.c" >/dev/null 2>&1)
+    gcc -O2 -fPIC -w -I"$PYINC" -c "$W/align.c" -o "$W/align.o"
+    gcc -shared -o "$W/giggles/align$EXT" "$W/align.o"
+    cp "$W/giggles/core$EXT" "$W/giggles/priorityqueue$EXT" "$W/giggles/align$EXT" "$OUT/pyref/giggles/"
     for f in __init__.py _version.py variant.py coverage.py graph.py; do cp "$W/giggles/$f" "$OUT/pyref/giggles/"; done
     rm -rf "$W"
     PYTHONPATH="$OUT/pyref" python3 -c "from giggles.core import GenotypeHMM, ReadSet, Read, Pedigree, NumericSampleIds, PhredGenotypeLikelihoods, Genotype; print('build_ref: giggles.core (reference) imports')"
