@@ -30,6 +30,7 @@
 #include "hmm_tma_kernel.cuh"
 #include "hmm_chain_kernel.cuh"
 #include "hmm_warp_kernel.cuh"
+#include "hmm_wave_kernel.cuh"
 #include "plan.hpp"
 #include "result.hpp"
 #include "schedule.hpp"
@@ -205,7 +206,7 @@ struct gg_hmm {
     Schedule sched;
     bool fp64 = false;
     bool shared_arena = false;   // GG_OPT_SHARED_ARENA: the state arena is borrowed per sweep
-    int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined, never two CTAs per SM, 3 = pipelined, never 16 consumer warps, 4 = no chain kernel, 5 = no warp-per-block kernel
+    int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined, never two CTAs per SM, 3 = pipelined, never 16 consumer warps, 4 = no chain kernel, 5 = no warp-per-block kernel (nor wave runs), 7 = no wave runs (small panels column by column)
     int device = 0;
     int num_sms = 0;
     size_t elem = 4;
@@ -223,7 +224,15 @@ struct gg_hmm {
     size_t tables_bytes = 0;
     DevBuf<unsigned int> d_counter;
     // runs of consecutive single-block columns fused into one chain-kernel launch each
-    struct Run { bool fwd; uint32_t first, n, max_classes; uint64_t in_off; int64_t in_col; };
+    struct Run { bool fwd; uint32_t first, n, max_classes; uint64_t in_off; int64_t in_col; bool wave; };
+    // wave runs (hmm_wave_kernel.cuh): consecutive small-panel steps of one direction in one cooperative launch
+    std::vector<Op> wave_ops;                 // the schedule ops behind the wave steps, in order (runs[].first indexes it)
+    std::vector<uint64_t> wave_w_off;         // per wave op: offset of its posterior partials (floats)
+    uint64_t wave_w_floats = 0;
+    uint32_t wave_grid = 0;
+    const void *wave_built_for = nullptr;     // state arena the device copy of the step arguments points into
+    DevBuf<unsigned char> d_wave_steps, d_wave_w, d_wave_sum;
+    DevBuf<unsigned int> d_wave_bar;
     std::vector<Run> runs;
     std::vector<ChainStep> chain_steps;
     DevBuf<ChainStep> d_chain_steps;
@@ -308,7 +317,8 @@ struct Engine {
     static uint64_t col_elems(uint32_t u, uint32_t R) { return block_stride(R) << u; }
     static uint64_t fg_elems(uint32_t u, uint32_t nA) { return ((uint64_t)2 * (nA + 1)) << u; }
 
-    static void launch_step(gg_hmm *h, const Op &op, bool fwd, bool init) {
+    // the kernel arguments of one column step of the schedule (pointers into the current state arena)
+    static StepArgs<T> make_args(gg_hmm *h, const Op &op, bool fwd, bool init) {
         const Plan &pl = h->plan;
         const uint32_t R = pl.n_haps;
         const uint32_t co = op.c;
@@ -371,6 +381,13 @@ struct Engine {
                 a.al_in = a.al_out;
             }
         }
+        return a;
+    }
+
+    static void launch_step(gg_hmm *h, const Op &op, bool fwd, bool init) {
+        const uint32_t R = h->plan.n_haps;
+        const ColumnPlan &pco = h->plan.cols[op.c];
+        const StepArgs<T> a = make_args(h, op, fwd, init);
         if (try_launch_warp(h, a, pco, fwd)) return;
         if (try_launch_tma(h, a, pco, fwd)) return;
         const uint32_t rpi = 32 / h->shape.G;
@@ -636,7 +653,101 @@ struct Engine {
         }
     }
 
+    // ---- wave kernel (hmm_wave_kernel.cuh): fuse consecutive steps of one direction over small panels (R <= 32)
+    static bool wave_eligible(const gg_hmm *h) {
+        return sizeof(T) == 4 && h->kernel_variant != 1 && h->kernel_variant != 5 && h->kernel_variant != 7 && h->plan.n_haps <= 32 &&
+               warp_kernel(true, h->shape.V, h->shape.G) != nullptr;
+    }
+    static const void *wave_kernel_ptr(bool fwd, int V, uint32_t G) {
+#define GG_WV(VV, GG) if (V == VV && G == GG) return fwd ? (const void *)wave_kernel<VV, GG, true> : (const void *)wave_kernel<VV, GG, false>;
+        GG_WV(2, 1) GG_WV(2, 2) GG_WV(2, 4) GG_WV(2, 8) GG_WV(2, 16) GG_WV(4, 1) GG_WV(4, 2) GG_WV(4, 4) GG_WV(4, 8)
+#undef GG_WV
+        return nullptr;
+    }
+
+    static void fuse_waves(gg_hmm *h) {
+        h->wave_ops.clear();
+        h->wave_w_off.clear();
+        h->wave_w_floats = 0;
+        if (!wave_eligible(h)) return;
+        const std::vector<Op> ops = h->exec_ops;
+        h->exec_ops.clear();
+        auto op_ok = [&](const Op &op) { return op.kind == OP_BWD || (op.kind == OP_FWD && op.c > 0); };
+        size_t i = 0;
+        while (i < ops.size()) {
+            if (!op_ok(ops[i])) { h->exec_ops.push_back(ops[i++]); continue; }
+            const bool fwd = ops[i].kind == OP_FWD;
+            size_t j = i;
+            while (j < ops.size() && op_ok(ops[j]) && (ops[j].kind == OP_FWD) == fwd &&
+                   (j == i || (fwd ? ops[j].c == ops[j - 1].c + 1 : (ops[j].c + 1 == ops[j - 1].c && ops[j].in_off == ops[j - 1].out_off))))
+                ++j;
+            // every eligible step goes through the wave kernel, single ones too: its summation orders depend on the
+            // wave grid only (problem and device), so the posteriors stay bit-identical across checkpoint schedules
+            gg_hmm::Run run{};
+            run.fwd = fwd;
+            run.wave = true;
+            run.first = (uint32_t)h->wave_ops.size();
+            run.n = (uint32_t)(j - i);
+            for (size_t q = i; q < j; ++q) {
+                h->wave_ops.push_back(ops[q]);
+                h->wave_w_off.push_back(h->wave_w_floats);
+                if (fwd) {
+                    const uint64_t nA = h->plan.cols[ops[q].c].n_alleles;
+                    h->wave_w_floats += nA * nA;          // per CTA; scaled by the grid at allocation
+                }
+            }
+            Op fused{};
+            fused.kind = OP_RUN;
+            fused.c = (uint32_t)h->runs.size();
+            h->runs.push_back(run);
+            h->exec_ops.push_back(fused);
+            i = j;
+        }
+    }
+
+    // device copy of the wave steps' arguments: they hold pointers into the state arena, so it is (re)built whenever
+    // the handle sweeps in another arena (shared-arena handles, a handle recreated on a cached arena)
+    static void upload_wave_steps(gg_hmm *h) {
+        if (h->wave_ops.empty() || h->wave_built_for == h->arena) return;
+        std::vector<WaveStep> steps(h->wave_ops.size());
+        for (size_t q = 0; q < steps.size(); ++q) {
+            const Op &op = h->wave_ops[q];
+            StepArgs<T> a = make_args(h, op, op.kind == OP_FWD, false);
+            std::memcpy(&steps[q].a, &a, sizeof(StepArgs<float>));
+            steps[q].w_off = h->wave_w_off[q] * h->wave_grid;
+            steps[q].pad = 0;
+        }
+        GG_CUDA(cudaMemcpyAsync(h->d_wave_steps.p, steps.data(), steps.size() * sizeof(WaveStep), cudaMemcpyHostToDevice, h->stream));
+        GG_CUDA(cudaStreamSynchronize(h->stream));      // `steps` is pageable and about to go away
+        h->wave_built_for = h->arena;
+    }
+
+    static void launch_wave(gg_hmm *h, const gg_hmm::Run &run) {
+        const int V = h->shape.V;
+        const uint32_t G = h->shape.G;
+        const void *k = wave_kernel_ptr(run.fwd, V, G);
+        WaveArgs w{};
+        w.steps = reinterpret_cast<const WaveStep *>(h->d_wave_steps.p) + run.first;
+        w.n_steps = run.n;
+        w.sum_partial = reinterpret_cast<float *>(h->d_wave_sum.p);
+        w.w_partial = reinterpret_cast<float *>(h->d_wave_w.p);
+        w.barrier = h->d_wave_bar.p;
+        GG_CUDA(cudaMemsetAsync(h->d_wave_bar.p, 0, sizeof(unsigned int), h->stream));
+        void *params[] = {(void *)&w};
+        GG_CUDA(cudaLaunchCooperativeKernel(k, dim3(h->wave_grid), dim3(32 * kWarpKernelWarps), params, 0, h->stream));
+        ++h->stats.n_launches;
+        if (run.fwd) {
+            wave_posterior_kernel<<<run.n, 32, 0, h->stream>>>(w.steps, run.n, w.w_partial, h->wave_grid);
+            GG_CUDA(cudaGetLastError());
+            ++h->stats.n_launches;
+        }
+    }
+
     static void launch_run(gg_hmm *h, const Op &op) {
+        if (h->runs[op.c].wave) {
+            launch_wave(h, h->runs[op.c]);
+            return;
+        }
         const gg_hmm::Run &run = h->runs[op.c];
         const uint32_t R = h->plan.n_haps;
         ChainArgs a{};
@@ -722,6 +833,7 @@ struct Engine {
             throw CudaError(m.find("budget") != std::string::npos ? GG_ERR_NOMEM : GG_ERR_INVALID, m);
         }
         fuse_runs(h);
+        fuse_waves(h);
     }
 
     // ---- device half: static tables H2D, arena
@@ -745,6 +857,23 @@ struct Engine {
         const size_t o_res = carve((size_t)pl.gl_offsets[C] * sizeof(double));
         const size_t o_cnt = carve(sizeof(unsigned int));
         const size_t o_part = carve((size_t)h->max_grid * kPartialStride * sizeof(T));
+        // wave runs: a grid that is co-resident (cooperative launch), two CTAs of the warp kernel's shape per SM at most
+        h->wave_grid = 0;
+        if (!h->wave_ops.empty()) {
+            int occ = 0;
+            GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wave_kernel_ptr(true, h->shape.V, h->shape.G), 32 * kWarpKernelWarps, 0));
+            int occ_b = 0;
+            GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, wave_kernel_ptr(false, h->shape.V, h->shape.G), 32 * kWarpKernelWarps, 0));
+            occ = std::min(occ, occ_b);
+            if (occ < 1) throw CudaError(GG_ERR_CUDA, "wave kernel does not fit on an SM");
+            const uint64_t max_items = (uint64_t)1 << pl.max_u;
+            h->wave_grid = (uint32_t)std::min<uint64_t>((uint64_t)h->num_sms * std::min(occ, 2),
+                                                       std::max<uint64_t>(1, (max_items + kWarpKernelWarps - 1) / kWarpKernelWarps));
+        }
+        const size_t o_wsteps = carve(h->wave_ops.size() * sizeof(WaveStep));
+        const size_t o_wsum = carve((size_t)2 * h->wave_grid * sizeof(float));
+        const size_t o_wbar = carve(sizeof(unsigned int));
+        const size_t o_ww = carve((size_t)h->wave_w_floats * h->wave_grid * sizeof(float));
         const size_t need = off + 256;
         h->tables = g_arena_cache.take(2 * h->device + 1, need, h->tables_bytes);
         if (!h->tables) {
@@ -764,6 +893,11 @@ struct Engine {
         h->d_result.bind(tb + o_res, pl.gl_offsets[C]);
         h->d_counter.bind(tb + o_cnt, 1);
         h->d_partial.bind(tb + o_part, (size_t)h->max_grid * kPartialStride * sizeof(T));
+        h->d_wave_steps.bind(tb + o_wsteps, h->wave_ops.size() * sizeof(WaveStep));
+        h->d_wave_sum.bind(tb + o_wsum, (size_t)2 * h->wave_grid * sizeof(float));
+        h->d_wave_bar.bind(tb + o_wbar, 1);
+        h->d_wave_w.bind(tb + o_ww, (size_t)h->wave_w_floats * h->wave_grid * sizeof(float));
+        h->wave_built_for = nullptr;
         h->d_cols.upload(h->host_cols, h->stream);
         h->d_em_side.upload(pl.em_side, h->stream);
         h->d_em_prob.upload(pl.em_prob, h->stream);
@@ -854,6 +988,7 @@ struct Engine {
             h->ev.resize(2 + 2 * nops);
             for (size_t i = old; i < h->ev.size(); ++i) GG_CUDA(cudaEventCreate(&h->ev[i]));
         }
+        upload_wave_steps(h);
         GG_CUDA(cudaEventRecord(h->ev[0], h->stream));
         launch_emax(h);
         for (size_t i = 0; i < nops; ++i) {
@@ -1275,7 +1410,7 @@ uint64_t gg_hmm_debug_op_times(gg_hmm *h, uint32_t *kind, uint32_t *column, floa
     for (size_t i = 0; i < n && i < cap; ++i) {
         const Op &op = h->exec_ops[i];
         kind[i] = (uint32_t)op.kind + (op.kind == OP_RUN && h->runs[op.c].fwd ? 100u : 0u);
-        column[i] = op.kind == OP_RUN ? h->chain_steps[h->runs[op.c].first].c_out : op.c;
+        column[i] = op.kind != OP_RUN ? op.c : (h->runs[op.c].wave ? h->wave_ops[h->runs[op.c].first].c : h->chain_steps[h->runs[op.c].first].c_out);
         ms[i] = h->op_ms[i];
     }
     return n;

@@ -14,20 +14,17 @@ namespace gg {
 
 constexpr int kWarpKernelWarps = 8;
 
+// One column step of one warp: the lane's column / row identities for this column pair, then its share of the
+// output blocks (items first_item, first_item + item_stride, ...).  Shared by the per-column kernel below and by the
+// multi-column wave kernel (hmm_wave_kernel.cuh).  qa: per-position posterior accumulators (forward), warp_sum: sum
+// of the produced column over this warp's items.
 template <int V, int G, bool FWD>
-__global__ void __launch_bounds__(32 * kWarpKernelWarps)
-step_warp_kernel(const StepArgs<float> a) {
-    typedef float T;
-    constexpr int NI = (V * G * G / 32) > 0 ? (V * G * G / 32) : 1;     // row iterations: ceil(R / (32/G)) for R <= V*G
-    extern __shared__ __align__(16) float s_pos[];      // forward: [warps][R*R] per-position posterior accumulators
-    __shared__ float s_sum[kWarpKernelWarps];
-    __shared__ double s_W[kPartialStride];
-    __shared__ double s_L[GG_MAX_ALLELES * (GG_MAX_ALLELES + 1) / 2];
-    __shared__ bool s_last;
-
-    const uint32_t R = a.R;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+__device__ __forceinline__ void warp_step(const StepArgs<float> &a, const float inv, const uint32_t first_item, const uint32_t item_stride,
+                                          float (&qa)[(V * G * G / 32) > 0 ? (V * G * G / 32) : 1][V], float &warp_sum) {
+    constexpr int NI = (V * G * G / 32) > 0 ? (V * G * G / 32) : 1;
+    const uint32_t lane = threadIdx.x & 31u;
     constexpr uint32_t rpi = 32u / G;
+    const uint32_t R = a.R;
     const uint32_t sub = lane / G, gl = lane % G;
     const uint32_t NCo = a.nA_out + 1, NCi = a.nA_in + 1;
     const uint32_t fgs_o = 2 * NCo, fgs_i = 2 * NCi;
@@ -61,21 +58,9 @@ step_warp_kernel(const StepArgs<float> a) {
         a1o[it] = rok[it] ? a.al_out[rowi[it]] : 0u;
         a1i[it] = (rok[it] && has_in) ? a.al_in[rowi[it]] : 0u;
     }
-    float qa[NI][V];
-#pragma unroll
-    for (int it = 0; it < NI; ++it)
-#pragma unroll
-        for (int v = 0; v < V; ++v) qa[it][v] = 0.f;
-
-    float inv = 1.f;
-    if (has_in) inv = (float)(1.0 / *a.in_scale);
     const float cA = (float)a.tA * inv, cB = (float)a.tB * inv, cC = (float)a.tC * inv;
-    float warp_sum = 0.f;     // FWD: sum of produced alpha; BWD: sum of produced beta
-    __syncthreads();
-
     const uint32_t n_items = 1u << a.u_out;
-    const uint32_t warps_total = gridDim.x * kWarpKernelWarps;
-    for (uint32_t item = blockIdx.x * kWarpKernelWarps + warp; item < n_items; item += warps_total) {
+    for (uint32_t item = first_item; item < n_items; item += item_stride) {
         const uint32_t lo = item & ((1u << n_bcast) - 1u), sh = item >> n_bcast;
         uint32_t b_out, b_in0;
         if (FWD) {
@@ -240,6 +225,48 @@ step_warp_kernel(const StepArgs<float> a) {
         // alleles sum(beta_{c-1}[b']) equals it exactly since tA + 2R tB + R^2 tC = 1; any positive scalar serves)
         warp_sum += FWD ? totacc : totv * inv;
     }
+
+}
+
+template <int V, int G, bool FWD>
+__global__ void __launch_bounds__(32 * kWarpKernelWarps)
+step_warp_kernel(const StepArgs<float> a) {
+    typedef float T;
+    constexpr int NI = (V * G * G / 32) > 0 ? (V * G * G / 32) : 1;     // row iterations: ceil(R / (32/G)) for R <= V*G
+    extern __shared__ __align__(16) float s_pos[];      // forward: [warps][R*R] per-position posterior accumulators
+    __shared__ float s_sum[kWarpKernelWarps];
+    __shared__ double s_W[kPartialStride];
+    __shared__ double s_L[GG_MAX_ALLELES * (GG_MAX_ALLELES + 1) / 2];
+    __shared__ bool s_last;
+
+    const uint32_t R = a.R;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    constexpr uint32_t rpi = 32u / G;
+    const uint32_t sub = lane / G, gl = lane % G;
+    const uint32_t NCo = a.nA_out + 1;
+    const uint64_t RR = (uint64_t)R * R;
+    const bool cok = gl * V < R;
+    const uint32_t ccol = cok ? gl * V : 0u;
+    const uint32_t n_iter = (R + rpi - 1) / rpi;
+    uint32_t rowi[NI];
+    bool rok[NI];
+#pragma unroll
+    for (int it = 0; it < NI; ++it) {
+        const uint32_t r = it * rpi + sub;
+        rok[it] = (uint32_t)it < n_iter && r < R;
+        rowi[it] = rok[it] ? r : 0u;
+    }
+    float qa[NI][V];
+#pragma unroll
+    for (int it = 0; it < NI; ++it)
+#pragma unroll
+        for (int v = 0; v < V; ++v) qa[it][v] = 0.f;
+
+    float inv = 1.f;
+    if (a.in != nullptr) inv = (float)(1.0 / *a.in_scale);
+    float warp_sum = 0.f;     // FWD: sum of produced alpha; BWD: sum of produced beta
+    __syncthreads();
+    warp_step<V, G, FWD>(a, inv, blockIdx.x * kWarpKernelWarps + warp, gridDim.x * kWarpKernelWarps, qa, warp_sum);
 
     // ---- kernel epilogue: per-position posterior accumulators -> (fixed-order fold over the warps) -> allele-class
     //      bins, one warp per class pair; CTA partials; last CTA.  No atomics: results are bit-reproducible.

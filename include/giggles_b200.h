@@ -78,7 +78,8 @@ typedef struct gg_options {
     uint64_t state_budget_bytes;      /* HBM budget for alpha/beta columns; 0 = 94 % of free memory when first asked; later calls
                                          reuse the retired arena of that size (gg_arena_release() makes the next call ask again) */
     int32_t precision;                /* 0 = fp32 state with per-column scaling (production); 1 = fp64 state (validation) */
-    int32_t kernel_variant;           /* 0 = auto; 1 = generic step kernel only (no bulk-copy pipeline), for A/B tests */
+    int32_t kernel_variant;           /* 0 = auto; for A/B tests: 1 = generic step kernel only (no bulk-copy pipeline), 4 = no chain
+                                         kernel, 5 = no warp-per-block kernel, 7 = small panels column by column (no wave runs) */
     uint32_t flags;                   /* GG_OPT_* */
 } gg_options;
 

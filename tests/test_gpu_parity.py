@@ -83,7 +83,8 @@ def test_fp64_mode_is_tight(i):
 
 def test_randomized_campaign_all_kernel_families():
     # seeded random shapes (panel size, coverage, tags, alleles, gaps, missing panel entries) through every kernel
-    # family: 0 = auto, 1 = generic, 2 = pipelined/one CTA per SM, 3 = no 16-warp variant, 4 = no chain kernel
+    # family: 0 = auto, 1 = generic, 2 = pipelined/one CTA per SM, 3 = no 16-warp variant, 4 = no chain kernel,
+    # 5 = no warp-per-block kernel, 7 = small panels column by column (no wave runs)
     rng = np.random.default_rng(2024)
     done = 0
     while done < 48:
@@ -102,7 +103,7 @@ def test_randomized_campaign_all_kernel_families():
         want = oracle.oracle_run(p)
         if np.isnan(want).any():
             continue
-        for kv in (0, 1, 2, 3, 4, 5):
+        for kv in (0, 1, 2, 3, 4, 5, 7):
             assert_posteriors_close(capi.hmm_run(p, device=0, kernel_variant=kv).values, want)
         done += 1
 
