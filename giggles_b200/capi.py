@@ -262,12 +262,12 @@ def _options(device=-1, budget=0, precision=0, kernel_variant=0, flags=0):
 
 
 def hmm_run(p: Problem | CProblem, device: int = -1, budget: int = 0, precision: int = 0,
-            kernel_variant: int = 0) -> Result:
+            kernel_variant: int = 0, shared_arena: bool = False) -> Result:
     """``gg_hmm_run``: host buffers in, host posteriors out (what ``new GenotypeHMM(...)`` does in the reference)."""
     cp = p if isinstance(p, CProblem) else CProblem(p)
     err = C.create_string_buffer(512)
     out = C.c_void_p()
-    o = _options(device, budget, precision, kernel_variant)
+    o = _options(device, budget, precision, kernel_variant, GG_OPT_SHARED_ARENA if shared_arena else 0)
     _check(lib().gg_hmm_run(C.byref(cp.struct), C.byref(o), C.byref(out), err, len(err)), err)
     return Result(out)
 

@@ -857,7 +857,7 @@ struct Engine {
         const size_t o_res = carve((size_t)pl.gl_offsets[C] * sizeof(double));
         const size_t o_cnt = carve(sizeof(unsigned int));
         const size_t o_part = carve((size_t)h->max_grid * kPartialStride * sizeof(T));
-        // wave runs: a grid that is co-resident (cooperative launch), two CTAs of the warp kernel's shape per SM at most
+        // wave runs: a grid that is co-resident (cooperative launch), as many CTAs per SM as the kernel is compiled for
         h->wave_grid = 0;
         if (!h->wave_ops.empty()) {
             int occ = 0;
@@ -867,7 +867,7 @@ struct Engine {
             occ = std::min(occ, occ_b);
             if (occ < 1) throw CudaError(GG_ERR_CUDA, "wave kernel does not fit on an SM");
             const uint64_t max_items = (uint64_t)1 << pl.max_u;
-            h->wave_grid = (uint32_t)std::min<uint64_t>((uint64_t)h->num_sms * std::min(occ, 2),
+            h->wave_grid = (uint32_t)std::min<uint64_t>((uint64_t)h->num_sms * std::min(occ, GG_WAVE_MIN_CTAS),
                                                        std::max<uint64_t>(1, (max_items + kWarpKernelWarps - 1) / kWarpKernelWarps));
         }
         const size_t o_wsteps = carve(h->wave_ops.size() * sizeof(WaveStep));

@@ -14,12 +14,15 @@ namespace gg {
 
 constexpr int kWarpKernelWarps = 8;
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // One column step of one warp: the lane's column / row identities for this column pair, then its share of the
 // output blocks (items first_item, first_item + item_stride, ...).  Shared by the per-column kernel below and by the
 // multi-column wave kernel (hmm_wave_kernel.cuh).  qa: per-position posterior accumulators (forward), warp_sum: sum
 // of the produced column over this warp's items.
 template <int V, int G, bool FWD>
-__device__ __forceinline__ void warp_step(const StepArgs<float> &a, const float inv, const uint32_t first_item, const uint32_t item_stride,
+__device__ __forceinline__ void warp_step(const StepArgs<float> &a, const uint8_t *al_out, const uint8_t *al_in, const float inv,
+                                          const uint32_t first_item, const uint32_t item_stride,
                                           float (&qa)[(V * G * G / 32) > 0 ? (V * G * G / 32) : 1][V], float &warp_sum) {
     constexpr int NI = (V * G * G / 32) > 0 ? (V * G * G / 32) : 1;
     const uint32_t lane = threadIdx.x & 31u;
@@ -43,8 +46,8 @@ __device__ __forceinline__ void warp_step(const StepArgs<float> &a, const float 
     uint32_t a2o[V], a2i[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        a2o[v] = cok ? a.al_out[ccol + v] : 0u;
-        a2i[v] = (cok && has_in) ? a.al_in[ccol + v] : 0u;
+        a2o[v] = cok ? al_out[ccol + v] : 0u;
+        a2i[v] = (cok && has_in) ? al_in[ccol + v] : 0u;
     }
     // per row slot: row index and its allele classes (fixed for the whole kernel)
     uint32_t rowi[NI], rowoff[NI], a1o[NI], a1i[NI];
@@ -55,8 +58,8 @@ __device__ __forceinline__ void warp_step(const StepArgs<float> &a, const float 
         rok[it] = (uint32_t)it < n_iter && r < R;
         rowi[it] = rok[it] ? r : 0u;
         rowoff[it] = rowi[it] * R;
-        a1o[it] = rok[it] ? a.al_out[rowi[it]] : 0u;
-        a1i[it] = (rok[it] && has_in) ? a.al_in[rowi[it]] : 0u;
+        a1o[it] = rok[it] ? al_out[rowi[it]] : 0u;
+        a1i[it] = (rok[it] && has_in) ? al_in[rowi[it]] : 0u;
     }
     const float cA = (float)a.tA * inv, cB = (float)a.tB * inv, cC = (float)a.tC * inv;
     const uint32_t n_items = 1u << a.u_out;
@@ -69,6 +72,28 @@ __device__ __forceinline__ void warp_step(const StepArgs<float> &a, const float 
         } else {
             b_out = (sh_id ? sh : dev_pdep(sh, a.shared_mask)) | (fr_id ? (lo << a.n_sh) : dev_pdep(lo, a.free_mask));
             b_in0 = sh;
+        }
+        if (nred == 1 && item + item_stride < n_items) {
+            // the next item's input block, beta block and F/G vectors on their way into L1 while this one is computed
+            // (columns of small panels sit in L2; a warp's items are otherwise a chain of exposed L2 round trips)
+            const uint32_t nx = item + item_stride;
+            const uint32_t nlo = nx & ((1u << n_bcast) - 1u), nsh = nx >> n_bcast;
+            uint32_t nb_out, nb_in;
+            if (FWD) {
+                nb_out = nsh | (nlo << a.n_sh);
+                nb_in = sh_id ? nsh : dev_pdep(nsh, a.shared_mask);
+            } else {
+                nb_out = (sh_id ? nsh : dev_pdep(nsh, a.shared_mask)) | (fr_id ? (nlo << a.n_sh) : dev_pdep(nlo, a.free_mask));
+                nb_in = nsh;
+            }
+            const uint32_t lines = (uint32_t)((BS * 4 + 127) / 128);
+            const char *pa = reinterpret_cast<const char *>(a.in + (uint64_t)nb_in * BS);
+            const char *pb = FWD ? reinterpret_cast<const char *>(a.beta + (uint64_t)nb_out * BS)
+                                 : reinterpret_cast<const char *>(a.fg_in + (uint64_t)nb_in * fgs_i);
+            if (lane < lines) prefetch_l1(pa + lane * 128);
+            else if (lane < 2 * lines && FWD) prefetch_l1(pb + (lane - lines) * 128);
+            else if (lane == 30 && !FWD) prefetch_l1(pb);
+            else if (lane == 31) prefetch_l1(a.fg_out + (uint64_t)nb_out * fgs_o);
         }
         const float *fgo = a.fg_out + (uint64_t)b_out * fgs_o;
         float colv[V], gout[V], gin0[V], colacc[V];
@@ -266,7 +291,7 @@ step_warp_kernel(const StepArgs<float> a) {
     if (a.in != nullptr) inv = (float)(1.0 / *a.in_scale);
     float warp_sum = 0.f;     // FWD: sum of produced alpha; BWD: sum of produced beta
     __syncthreads();
-    warp_step<V, G, FWD>(a, inv, blockIdx.x * kWarpKernelWarps + warp, gridDim.x * kWarpKernelWarps, qa, warp_sum);
+    warp_step<V, G, FWD>(a, a.al_out, a.al_in, inv, blockIdx.x * kWarpKernelWarps + warp, gridDim.x * kWarpKernelWarps, qa, warp_sum);
 
     // ---- kernel epilogue: per-position posterior accumulators -> (fixed-order fold over the warps) -> allele-class
     //      bins, one warp per class pair; CTA partials; last CTA.  No atomics: results are bit-reproducible.

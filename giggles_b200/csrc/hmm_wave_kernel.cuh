@@ -19,6 +19,10 @@
 #pragma once
 #include "hmm_warp_kernel.cuh"
 
+#ifndef GG_WAVE_MIN_CTAS
+#define GG_WAVE_MIN_CTAS 2
+#endif
+
 namespace gg {
 
 struct WaveStep {
@@ -53,7 +57,7 @@ __device__ __forceinline__ void wave_barrier(unsigned int *bar, unsigned int tar
 }
 
 template <int V, int G, bool FWD>
-__global__ void __launch_bounds__(32 * kWarpKernelWarps)
+__global__ void __launch_bounds__(32 * kWarpKernelWarps, GG_WAVE_MIN_CTAS)
 wave_kernel(const WaveArgs w) {
     constexpr int NI = (V * G * G / 32) > 0 ? (V * G * G / 32) : 1;
     __shared__ float s_sum[kWarpKernelWarps];
@@ -64,9 +68,31 @@ wave_kernel(const WaveArgs w) {
     const uint32_t sub = lane / G, gl = lane % G;
     const uint32_t first_item = blockIdx.x * kWarpKernelWarps + warp, item_stride = gridDim.x * kWarpKernelWarps;
 
+    // step arguments and the two allele vectors are staged in shared memory one step ahead (the grid barrier's acquire
+    // drops the L1 contents, so without this every step would begin with two dependent L2 round trips)
+    __shared__ __align__(16) WaveStep s_step[2];
+    __shared__ uint8_t s_al[2][2][32];
+    auto stage_args = [&](uint32_t s, uint32_t slot) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(w.steps + s);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_step[slot]);
+        if (tid < sizeof(WaveStep) / 4) dst[tid] = __ldcg(src + tid);
+    };
+    auto stage_alleles = [&](uint32_t slot) {       // after a __syncthreads that follows stage_args(slot)
+        const StepArgs<float> &n = s_step[slot].a;
+        if (tid < 32) s_al[slot][0][tid] = tid < n.R ? n.al_out[tid] : (uint8_t)0;
+        else if (tid < 64) s_al[slot][1][tid - 32] = tid - 32 < n.R ? n.al_in[tid - 32] : (uint8_t)0;
+    };
+    stage_args(0, 0);
+    __syncthreads();
+    stage_alleles(0);
+    __syncthreads();
+
     float inv = 1.f;
     for (uint32_t s = 0; s < w.n_steps; ++s) {
-        const StepArgs<float> &a = w.steps[s].a;
+        const uint32_t slot = s & 1u;
+        const StepArgs<float> &a = s_step[slot].a;
+        const uint8_t *al_out = s_al[slot][0], *al_in = s_al[slot][1];
+        if (s + 1 < w.n_steps) stage_args(s + 1, slot ^ 1u);      // visible after the __syncthreads before the barrier
         if (s == 0) inv = (float)(1.0 / *a.in_scale);
         float qa[NI][V];
 #pragma unroll
@@ -74,7 +100,7 @@ wave_kernel(const WaveArgs w) {
 #pragma unroll
             for (int v = 0; v < V; ++v) qa[it][v] = 0.f;
         float warp_sum = 0.f;
-        warp_step<V, G, FWD>(a, inv, first_item, item_stride, qa, warp_sum);
+        warp_step<V, G, FWD>(a, al_out, al_in, inv, first_item, item_stride, qa, warp_sum);
 
         if (FWD) {
             // posterior partials of this warp: sum of the accumulators per (row allele, column allele), alleles 1-based
@@ -85,11 +111,11 @@ wave_kernel(const WaveArgs w) {
             const uint32_t n_iter = (R + rpi - 1) / rpi;
             uint32_t cls_c[V], cls_r[NI];
 #pragma unroll
-            for (int v = 0; v < V; ++v) cls_c[v] = cok ? a.al_out[ccol + v] : 0u;
+            for (int v = 0; v < V; ++v) cls_c[v] = cok ? al_out[ccol + v] : 0u;
 #pragma unroll
             for (int it = 0; it < NI; ++it) {
                 const uint32_t r = it * rpi + sub;
-                cls_r[it] = ((uint32_t)it < n_iter && r < R && cok) ? a.al_out[r] : 0u;
+                cls_r[it] = ((uint32_t)it < n_iter && r < R && cok) ? al_out[r] : 0u;
             }
             for (uint32_t i = 1; i <= nA; ++i)
                 for (uint32_t j = 1; j <= nA; ++j) {
@@ -105,9 +131,10 @@ wave_kernel(const WaveArgs w) {
         }
         if (lane == 0) s_sum[warp] = warp_sum;
         __syncthreads();
+        if (s + 1 < w.n_steps) stage_alleles(slot ^ 1u);          // next step's arguments are in place since the barrier above
         if (FWD) {
             const uint32_t nA = a.nA_out;
-            float *dst = w.w_partial + w.steps[s].w_off + (uint64_t)blockIdx.x * nA * nA;
+            float *dst = w.w_partial + s_step[slot].w_off + (uint64_t)blockIdx.x * nA * nA;
             for (uint32_t p = tid; p < nA * nA; p += blockDim.x) {
                 float q = 0.f;
 #pragma unroll
