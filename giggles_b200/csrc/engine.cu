@@ -658,9 +658,12 @@ struct Engine {
         return sizeof(T) == 4 && h->kernel_variant != 1 && h->kernel_variant != 5 && h->kernel_variant != 7 && h->plan.n_haps <= 32 &&
                warp_kernel(true, h->shape.V, h->shape.G) != nullptr;
     }
-    static const void *wave_kernel_ptr(bool fwd, int V, uint32_t G) {
-#define GG_WV(VV, GG) if (V == VV && G == GG) return fwd ? (const void *)wave_kernel<VV, GG, true> : (const void *)wave_kernel<VV, GG, false>;
-        GG_WV(2, 1) GG_WV(2, 2) GG_WV(2, 4) GG_WV(2, 8) GG_WV(2, 16) GG_WV(4, 1) GG_WV(4, 2) GG_WV(4, 4) GG_WV(4, 8)
+    // panels of an even number of haplotypes up to 16 get the thread-per-block path inside the wave kernel
+    static const void *wave_kernel_ptr(bool fwd, int V, uint32_t G, uint32_t R) {
+#define GG_WV(VV, GG, RL) if (V == VV && G == GG && rl == RL) return fwd ? (const void *)wave_kernel<VV, GG, true, RL> : (const void *)wave_kernel<VV, GG, false, RL>;
+        const uint32_t rl = (R % 2 == 0 && R <= 16) ? R : 0;
+        GG_WV(2, 1, 2) GG_WV(4, 1, 4) GG_WV(2, 4, 6) GG_WV(4, 2, 8) GG_WV(2, 8, 10) GG_WV(4, 4, 12) GG_WV(2, 8, 14) GG_WV(4, 4, 16)
+        GG_WV(2, 1, 0) GG_WV(2, 2, 0) GG_WV(2, 4, 0) GG_WV(2, 8, 0) GG_WV(2, 16, 0) GG_WV(4, 1, 0) GG_WV(4, 2, 0) GG_WV(4, 4, 0) GG_WV(4, 8, 0)
 #undef GG_WV
         return nullptr;
     }
@@ -725,7 +728,7 @@ struct Engine {
     static void launch_wave(gg_hmm *h, const gg_hmm::Run &run) {
         const int V = h->shape.V;
         const uint32_t G = h->shape.G;
-        const void *k = wave_kernel_ptr(run.fwd, V, G);
+        const void *k = wave_kernel_ptr(run.fwd, V, G, h->plan.n_haps);
         WaveArgs w{};
         w.steps = reinterpret_cast<const WaveStep *>(h->d_wave_steps.p) + run.first;
         w.n_steps = run.n;
@@ -861,9 +864,9 @@ struct Engine {
         h->wave_grid = 0;
         if (!h->wave_ops.empty()) {
             int occ = 0;
-            GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wave_kernel_ptr(true, h->shape.V, h->shape.G), 32 * kWarpKernelWarps, 0));
+            GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wave_kernel_ptr(true, h->shape.V, h->shape.G, pl.n_haps), 32 * kWarpKernelWarps, 0));
             int occ_b = 0;
-            GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, wave_kernel_ptr(false, h->shape.V, h->shape.G), 32 * kWarpKernelWarps, 0));
+            GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, wave_kernel_ptr(false, h->shape.V, h->shape.G, pl.n_haps), 32 * kWarpKernelWarps, 0));
             occ = std::min(occ, occ_b);
             if (occ < 1) throw CudaError(GG_ERR_CUDA, "wave kernel does not fit on an SM");
             const uint64_t max_items = (uint64_t)1 << pl.max_u;

@@ -20,7 +20,7 @@
 #include "hmm_warp_kernel.cuh"
 
 #ifndef GG_WAVE_MIN_CTAS
-#define GG_WAVE_MIN_CTAS 2
+#define GG_WAVE_MIN_CTAS 1
 #endif
 
 namespace gg {
@@ -39,9 +39,9 @@ struct WaveArgs {
     unsigned int *barrier;        // arrival counter, zero at launch
 };
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
     unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -51,12 +51,199 @@ __device__ __forceinline__ void wave_barrier(unsigned int *bar, unsigned int tar
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(bar, 1u);
-        while (ld_acquire_u32(bar) < target) { }
+        // poll relaxed and fence once: an acquire load per poll would drop the SM's L1 contents on every iteration
+        // (ncu: CCTL.IVALL executed 20 M times per run) while the other warps of the CTA are still working
+        while (ld_relaxed_u32(bar) < target) { }
+        __threadfence();
     }
     __syncthreads();
 }
 
-template <int V, int G, bool FWD>
+
+constexpr int kLaneMaxAlleles = 4;     // forward lane path: posterior bins per thread are kLaneMaxAlleles^2 registers
+
+// Thread-per-block column step for very small panels (R even, <= 16; configs[0] has R = 10).  With one warp per block
+// (warp_step) a 100-value block costs ~500 warp instructions, most of them index arithmetic, predicates and shuffles
+// for 39 % busy lanes.  Here ONE THREAD owns a whole bipartition block: row sums, column sums and the block total are
+// plain register arithmetic (no shuffles), two rows at a time move as R/2 128-bit accesses, and a warp advances 32
+// blocks at once.  Neighbouring lanes work on neighbouring blocks (496 bytes apart for R = 10), so a warp's accesses
+// walk 32 lines that L1 holds across the row loop.  Same arithmetic as warp_step; summation orders differ.
+//   W: this thread's posterior sums per (row allele, column allele), alleles < kLaneMaxAlleles (forward only);
+//   sum_acc: this thread's share of the produced column's sum.
+template <int R, bool FWD>
+__device__ __forceinline__ void lane_step(const StepArgs<float> &a, const uint8_t *al_o, const uint8_t *al_i, const float inv,
+                                          const uint32_t first_item, const uint32_t item_stride,
+                                          float (&W)[kLaneMaxAlleles][kLaneMaxAlleles], float &sum_acc) {
+    static_assert(R % 2 == 0 && R >= 2 && R <= 16, "lane_step: even panels up to 16 haplotypes");
+    constexpr uint32_t RR = R * R, o_row = RR, o_col = RR + R, o_tot = RR + 2 * R;
+    constexpr int NV = R / 2;                      // float4 per pair of rows
+    const uint32_t BS = a.BS;
+    const uint32_t NCo = a.nA_out + 1, NCi = a.nA_in + 1, fgs_o = 2 * NCo, fgs_i = 2 * NCi, nA = a.nA_out;
+    const uint32_t nred = FWD ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
+    const uint32_t n_bcast = FWD ? (a.u_out - a.n_sh) : a.n_free_left;
+    const bool sh_id = a.shared_mask == ((a.n_sh >= 32 ? 0u : (1u << a.n_sh)) - 1u);
+    const bool fr_id = a.free_mask == ((((a.n_free_left >= 32 ? 0u : (1u << a.n_free_left)) - 1u)) << a.n_sh);
+    const float cA = (float)a.tA * inv, cB = (float)a.tB * inv, cC = (float)a.tC * inv;
+    const uint32_t n_items = 1u << a.u_out;
+    uint32_t co[R], ci[R];                         // allele classes of the columns (the same in every thread)
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        co[j] = al_o[j];
+        ci[j] = al_i[j];
+    }
+    for (uint32_t item = first_item; item < n_items; item += item_stride) {
+        const uint32_t lo = item & ((1u << n_bcast) - 1u), sh = item >> n_bcast;
+        uint32_t b_out, b_in0;
+        if (FWD) {
+            b_out = sh | (lo << a.n_sh);
+            b_in0 = sh_id ? sh : dev_pdep(sh, a.shared_mask);
+        } else {
+            b_out = (sh_id ? sh : dev_pdep(sh, a.shared_mask)) | (fr_id ? (lo << a.n_sh) : dev_pdep(lo, a.free_mask));
+            b_in0 = sh;
+        }
+        const float *fgo = a.fg_out + (uint64_t)b_out * fgs_o;
+        float g[R], cb[R], colacc[R], gk0[R];
+        float totv = 0.f;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            g[j] = fgo[NCo + co[j]];
+            cb[j] = 0.f;
+            colacc[j] = 0.f;
+            gk0[j] = 1.f;
+        }
+        {   // column sums and total of the reduced input
+            uint32_t subm = 0;
+            for (uint32_t k = 0; k < nred; ++k) {
+                const uint64_t bk = FWD ? (uint64_t)(b_in0 | subm) : (uint64_t)(b_in0 | (k << a.n_sh));
+                subm = (subm - a.free_mask) & a.free_mask;
+                const float *blk = a.in + bk * BS;
+#pragma unroll
+                for (int j = 0; j < R; j += 2) {
+                    const float2 t = *reinterpret_cast<const float2 *>(blk + o_col + j);
+                    cb[j] += t.x;
+                    cb[j + 1] += t.y;
+                }
+                totv += blk[o_tot];
+            }
+        }
+        const float ctot = cC * totv;
+#pragma unroll
+        for (int j = 0; j < R; ++j) cb[j] = fmaf(cB, cb[j], ctot);
+        if (!FWD && nred == 1) {
+            const float *fgi = a.fg_in + (uint64_t)b_in0 * fgs_i;
+#pragma unroll
+            for (int j = 0; j < R; ++j) gk0[j] = fgi[NCi + ci[j]];
+        }
+        float *outp = a.out + (uint64_t)b_out * BS;
+        const float *bblk = FWD ? a.beta + (uint64_t)b_out * BS : nullptr;
+        float tot = 0.f;
+        for (uint32_t r = 0; r < R; r += 2) {
+            float x[2 * R], rowv0 = 0.f, rowv1 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 2 * R; ++e) x[e] = 0.f;
+            const uint32_t ai0 = al_i[r], ai1 = al_i[r + 1];
+            uint32_t subm = 0;
+            for (uint32_t k = 0; k < nred; ++k) {
+                const uint64_t bk = FWD ? (uint64_t)(b_in0 | subm) : (uint64_t)(b_in0 | (k << a.n_sh));
+                subm = (subm - a.free_mask) & a.free_mask;
+                const float *blk = a.in + bk * BS;
+                const float2 rv = *reinterpret_cast<const float2 *>(blk + o_row + r);
+                rowv0 += rv.x;
+                rowv1 += rv.y;
+                float fk0 = 1.f, fk1 = 1.f;
+                const float *fgk = nullptr;
+                if (!FWD) {
+                    fgk = a.fg_in + bk * fgs_i;
+                    fk0 = fgk[ai0];
+                    fk1 = fgk[ai1];
+                }
+                const float4 *src = reinterpret_cast<const float4 *>(blk + r * R);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const float4 t = src[v];
+                    const float ld[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        constexpr int dummy = 0; (void)dummy;
+                        const int e = 4 * v + q, j = e % R;
+                        if (FWD) {
+                            x[e] += ld[q];
+                        } else {
+                            const float gk = nred == 1 ? gk0[j] : fgk[NCi + ci[j]];
+                            x[e] = fmaf(ld[q], (e < R ? fk0 : fk1) * gk, x[e]);
+                        }
+                    }
+                }
+            }
+            float xo[2 * R], rs[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const uint32_t ao = al_o[r + q];
+                const float fo = fgo[ao];
+                const float rowterm = cB * (q == 0 ? rowv0 : rowv1);
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const float base = fmaf(cA, x[q * R + j], rowterm + cb[j]);
+                    float o, w;
+                    if (FWD) {
+                        o = (fo * g[j]) * base;
+                        w = o;
+                    } else {
+                        o = (ao != 0 && co[j] != 0) ? base : 0.f;
+                        w = o * (fo * g[j]);
+                    }
+                    acc += w;
+                    colacc[j] += w;
+                    xo[q * R + j] = o;
+                }
+                rs[q] = acc;
+                tot += acc;
+            }
+            float4 *dst = reinterpret_cast<float4 *>(outp + r * R);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) dst[v] = make_float4(xo[4 * v], xo[4 * v + 1], xo[4 * v + 2], xo[4 * v + 3]);
+            *reinterpret_cast<float2 *>(outp + o_row + r) = make_float2(rs[0], rs[1]);
+            if (FWD) {
+                const float4 *bsrc = reinterpret_cast<const float4 *>(bblk + r * R);
+                float rowc[2][kLaneMaxAlleles];
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int c = 0; c < kLaneMaxAlleles; ++c) rowc[q][c] = 0.f;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const float4 t = bsrc[v];
+                    const float bv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int e = 4 * v + q, j = e % R;
+                        const float fb = xo[e] * bv[q];
+#pragma unroll
+                        for (int c = 0; c < kLaneMaxAlleles; ++c)
+                            if ((uint32_t)c < nA) rowc[e < R ? 0 : 1][c] += (co[j] == (uint32_t)c + 1) ? fb : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const uint32_t ao = al_o[r + q];
+#pragma unroll
+                    for (int i = 0; i < kLaneMaxAlleles; ++i)
+#pragma unroll
+                        for (int c = 0; c < kLaneMaxAlleles; ++c)
+                            if ((uint32_t)i < nA && (uint32_t)c < nA) W[i][c] += (ao == (uint32_t)i + 1) ? rowc[q][c] : 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < R; j += 2) *reinterpret_cast<float2 *>(outp + o_col + j) = make_float2(colacc[j], colacc[j + 1]);
+        outp[o_tot] = tot;
+        sum_acc += FWD ? tot : totv * inv;
+    }
+}
+
+// RL: the panel size when the thread-per-block path (lane_step) applies to it, else 0
+template <int V, int G, bool FWD, int RL>
 __global__ void __launch_bounds__(32 * kWarpKernelWarps, GG_WAVE_MIN_CTAS)
 wave_kernel(const WaveArgs w) {
     constexpr int NI = (V * G * G / 32) > 0 ? (V * G * G / 32) : 1;
@@ -94,12 +281,41 @@ wave_kernel(const WaveArgs w) {
         const uint8_t *al_out = s_al[slot][0], *al_in = s_al[slot][1];
         if (s + 1 < w.n_steps) stage_args(s + 1, slot ^ 1u);      // visible after the __syncthreads before the barrier
         if (s == 0) inv = (float)(1.0 / *a.in_scale);
+        float warp_sum = 0.f;
+        const bool lane_path = RL > 0 && (!FWD || a.nA_out <= (uint32_t)kLaneMaxAlleles);
+        if (lane_path) {
+            // thread-per-block: warp tasks of 32 consecutive blocks, dealt round-robin over the CTAs first so that a
+            // column of a few thousand blocks still spreads over all SMs
+            constexpr int RLL = RL > 0 ? RL : 2;
+            float W[kLaneMaxAlleles][kLaneMaxAlleles];
+#pragma unroll
+            for (int i = 0; i < kLaneMaxAlleles; ++i)
+#pragma unroll
+                for (int j = 0; j < kLaneMaxAlleles; ++j) W[i][j] = 0.f;
+            float sum_acc = 0.f;
+            lane_step<RLL, FWD>(a, al_out, al_in, inv, (blockIdx.x + gridDim.x * warp) * 32u + lane, gridDim.x * kWarpKernelWarps * 32u, W, sum_acc);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sum_acc += __shfl_xor_sync(0xffffffffu, sum_acc, o);
+            warp_sum = sum_acc;
+            if (FWD) {
+                const uint32_t nA = a.nA_out;
+#pragma unroll
+                for (int i = 0; i < kLaneMaxAlleles; ++i)
+#pragma unroll
+                    for (int j = 0; j < kLaneMaxAlleles; ++j)
+                        if ((uint32_t)i < nA && (uint32_t)j < nA) {
+                            float q = W[i][j];
+#pragma unroll
+                            for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                            if (lane == 0) s_w[warp][i * nA + j] = q;
+                        }
+            }
+        } else {
         float qa[NI][V];
 #pragma unroll
         for (int it = 0; it < NI; ++it)
 #pragma unroll
             for (int v = 0; v < V; ++v) qa[it][v] = 0.f;
-        float warp_sum = 0.f;
         warp_step<V, G, FWD>(a, al_out, al_in, inv, first_item, item_stride, qa, warp_sum);
 
         if (FWD) {
@@ -128,6 +344,7 @@ wave_kernel(const WaveArgs w) {
                     for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
                     if (lane == 0) s_w[warp][(i - 1) * nA + (j - 1)] = q;
                 }
+        }
         }
         if (lane == 0) s_sum[warp] = warp_sum;
         __syncthreads();
