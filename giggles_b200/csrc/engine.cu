@@ -719,6 +719,11 @@ struct Engine {
             std::memcpy(&steps[q].a, &a, sizeof(StepArgs<float>));
             steps[q].w_off = h->wave_w_off[q] * h->wave_grid;
             steps[q].pad = 0;
+            const uint32_t Rl = h->plan.n_haps;
+            const uint32_t c_in = op.kind == OP_FWD ? op.c - 1 : op.c + 1;
+            std::memset(steps[q].al_out, 0, 64);
+            std::memcpy(steps[q].al_out, h->plan.allele1.data() + (size_t)op.c * Rl, Rl);
+            std::memcpy(steps[q].al_in, h->plan.allele1.data() + (size_t)c_in * Rl, Rl);
         }
         GG_CUDA(cudaMemcpyAsync(h->d_wave_steps.p, steps.data(), steps.size() * sizeof(WaveStep), cudaMemcpyHostToDevice, h->stream));
         GG_CUDA(cudaStreamSynchronize(h->stream));      // `steps` is pageable and about to go away
@@ -732,10 +737,9 @@ struct Engine {
         WaveArgs w{};
         w.steps = reinterpret_cast<const WaveStep *>(h->d_wave_steps.p) + run.first;
         w.n_steps = run.n;
-        w.sum_partial = reinterpret_cast<float *>(h->d_wave_sum.p);
         w.w_partial = reinterpret_cast<float *>(h->d_wave_w.p);
-        w.barrier = h->d_wave_bar.p;
-        GG_CUDA(cudaMemsetAsync(h->d_wave_bar.p, 0, sizeof(unsigned int), h->stream));
+        w.barrier = reinterpret_cast<unsigned long long *>(h->d_wave_bar.p);
+        GG_CUDA(cudaMemsetAsync(h->d_wave_bar.p, 0, 3 * sizeof(unsigned long long), h->stream));
         void *params[] = {(void *)&w};
         GG_CUDA(cudaLaunchCooperativeKernel(k, dim3(h->wave_grid), dim3(32 * kWarpKernelWarps), params, 0, h->stream));
         ++h->stats.n_launches;
@@ -875,7 +879,7 @@ struct Engine {
         }
         const size_t o_wsteps = carve(h->wave_ops.size() * sizeof(WaveStep));
         const size_t o_wsum = carve((size_t)2 * h->wave_grid * sizeof(float));
-        const size_t o_wbar = carve(sizeof(unsigned int));
+        const size_t o_wbar = carve(3 * sizeof(unsigned long long));
         const size_t o_ww = carve((size_t)h->wave_w_floats * h->wave_grid * sizeof(float));
         const size_t need = off + 256;
         h->tables = g_arena_cache.take(2 * h->device + 1, need, h->tables_bytes);
@@ -898,7 +902,7 @@ struct Engine {
         h->d_partial.bind(tb + o_part, (size_t)h->max_grid * kPartialStride * sizeof(T));
         h->d_wave_steps.bind(tb + o_wsteps, h->wave_ops.size() * sizeof(WaveStep));
         h->d_wave_sum.bind(tb + o_wsum, (size_t)2 * h->wave_grid * sizeof(float));
-        h->d_wave_bar.bind(tb + o_wbar, 1);
+        h->d_wave_bar.bind(tb + o_wbar, 6);
         h->d_wave_w.bind(tb + o_ww, (size_t)h->wave_w_floats * h->wave_grid * sizeof(float));
         h->wave_built_for = nullptr;
         h->d_cols.upload(h->host_cols, h->stream);

@@ -7,9 +7,10 @@
 // as the per-column kernel (warp_step, hmm_warp_kernel.cuh), the CTAs meet at a grid barrier (one atomic arrival
 // counter, acquire / release), and the next step starts.  What a launch boundary used to provide is done in place:
 //
-//   column scale   every CTA leaves the sum of what it produced in a double-buffered slot; after the barrier each CTA
-//                  adds the slots up in the same fixed order, so all of them fold the same 1/sum into the next step
-//                  (CTA 0 also stores it where later launches expect it);
+//   column scale   every CTA arrives at the barrier with its share of the produced column's sum in fixed point, in the
+//                  same 64-bit atomic add that counts the arrival; integer addition is order-independent, so all CTAs
+//                  read the same total and fold the same 1/sum into the next step (CTA 0 also stores it where later
+//                  launches expect it);
 //   posterior      forward steps bin their per-position accumulators by allele-class pair in registers (the class of a
 //                  (row, column) position is the same for every block of a column), one partial vector per CTA and
 //                  step; wave_posterior_kernel adds them up in fixed order after the run.
@@ -29,36 +30,47 @@ struct WaveStep {
     StepArgs<float> a;
     uint64_t w_off;       // forward: offset (floats) of this step's [grid][nA_out^2] posterior partials
     uint64_t pad;
+    uint8_t al_out[32], al_in[32];   // allele + 1 of the produced / input column (R <= 32), so that one record is all a step needs
 };
+static_assert(sizeof(WaveStep) % 16 == 0, "WaveStep is staged with 32-bit copies and kept 16-byte aligned");
 
 struct WaveArgs {
     const WaveStep *steps;
     uint32_t n_steps;
-    float *sum_partial;           // [2][gridDim.x]
     float *w_partial;             // forward: posterior partials of every step
-    unsigned int *barrier;        // arrival counter, zero at launch
+    unsigned long long *barrier;  // [3] arrivals << 52 | fixed-point column sum, zero at launch; step s uses slot s % 3
 };
 
-__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
-// all CTAs of the (co-resident, cooperatively launched) grid; `target` = arrivals expected so far
-__device__ __forceinline__ void wave_barrier(unsigned int *bar, unsigned int target) {
+// Grid barrier of the (co-resident, cooperatively launched) grid that also adds up the column sum: every CTA arrives
+// with ONE 64-bit atomic add of (1 << 52 | its share of the sum in 2^-32 fixed point).  Integer addition does not depend
+// on the order of arrival, so every CTA reads the same total whatever the timing - the scale of the next step costs no
+// memory round trip of its own and stays bit-reproducible.  (The sum only has to be a consistent positive scale; 2^-32
+// resolution against column sums of order one is ample.)  Thread 0 polls relaxed and fences once: an acquire load per
+// poll would drop the SM's L1 contents on every iteration.  Three slots in rotation; CTA 0 clears the slot of the step
+// before, which every CTA has left by then and nobody reaches again before CTA 0's next arrival.  Returns the total.
+__device__ __forceinline__ double wave_barrier_sum(unsigned long long *bar, const uint32_t step, const float cta_sum, double *s_total) {
     __syncthreads();
     if (threadIdx.x == 0) {
+        const double clamped = fmin(fmax((double)cta_sum, 0.0), 1024.0);
+        const unsigned long long mine = (1ull << 52) | (unsigned long long)__double2ll_rn(clamped * 4294967296.0);
+        unsigned long long *slot = bar + step % 3u;
         __threadfence();
-        atomicAdd(bar, 1u);
-        // poll relaxed and fence once: an acquire load per poll would drop the SM's L1 contents on every iteration
-        // (ncu: CCTL.IVALL executed 20 M times per run) while the other warps of the CTA are still working
-        while (ld_relaxed_u32(bar) < target) { }
+        atomicAdd(slot, mine);
+        unsigned long long v;
+        do { v = ld_relaxed_u64(slot); } while ((v >> 52) < gridDim.x);
         __threadfence();
+        if (blockIdx.x == 0) bar[(step + 2u) % 3u] = 0ull;
+        *s_total = (double)(v & ((1ull << 52) - 1ull)) * (1.0 / 4294967296.0);
     }
     __syncthreads();
+    return *s_total;
 }
-
 
 constexpr int kLaneMaxAlleles = 4;     // forward lane path: posterior bins per thread are kLaneMaxAlleles^2 registers
 
@@ -136,7 +148,20 @@ __device__ __forceinline__ void lane_step(const StepArgs<float> &a, const uint8_
         }
         float *outp = a.out + (uint64_t)b_out * BS;
         const float *bblk = FWD ? a.beta + (uint64_t)b_out * BS : nullptr;
+        if (nred == 1) {
+            // every line of the input block (and of beta, which comes from HBM) on its way to L1 before the row loop
+            // walks them: one exposed round trip per block instead of one per pair of rows
+            constexpr int kLines = (int)((RR + 2 * R + 4 + 3) / 4 * 16 + 127) / 128 + 1;
+            const char *pi = reinterpret_cast<const char *>(a.in + (uint64_t)b_in0 * BS);
+#pragma unroll
+            for (int l = 0; l < kLines; ++l) prefetch_l1(pi + l * 128);
+            if (FWD) {
+#pragma unroll
+                for (int l = 0; l < kLines; ++l) prefetch_l1(reinterpret_cast<const char *>(bblk) + l * 128);
+            }
+        }
         float tot = 0.f;
+#pragma unroll
         for (uint32_t r = 0; r < R; r += 2) {
             float x[2 * R], rowv0 = 0.f, rowv1 = 0.f;
 #pragma unroll
@@ -248,37 +273,29 @@ __global__ void __launch_bounds__(32 * kWarpKernelWarps, GG_WAVE_MIN_CTAS)
 wave_kernel(const WaveArgs w) {
     constexpr int NI = (V * G * G / 32) > 0 ? (V * G * G / 32) : 1;
     __shared__ float s_sum[kWarpKernelWarps];
-    __shared__ float s_inv;
     __shared__ float s_w[FWD ? kWarpKernelWarps : 1][FWD ? GG_MAX_ALLELES * GG_MAX_ALLELES : 1];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     constexpr uint32_t rpi = 32u / G;
     const uint32_t sub = lane / G, gl = lane % G;
     const uint32_t first_item = blockIdx.x * kWarpKernelWarps + warp, item_stride = gridDim.x * kWarpKernelWarps;
 
-    // step arguments and the two allele vectors are staged in shared memory one step ahead (the grid barrier's acquire
-    // drops the L1 contents, so without this every step would begin with two dependent L2 round trips)
+    // the step record (arguments and the two allele vectors) is staged in shared memory one step ahead: the barrier's
+    // acquire drops the L1 contents, so without this every step would begin with dependent L2 round trips
     __shared__ __align__(16) WaveStep s_step[2];
-    __shared__ uint8_t s_al[2][2][32];
+    __shared__ double s_total;
     auto stage_args = [&](uint32_t s, uint32_t slot) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(w.steps + s);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&s_step[slot]);
         if (tid < sizeof(WaveStep) / 4) dst[tid] = __ldcg(src + tid);
     };
-    auto stage_alleles = [&](uint32_t slot) {       // after a __syncthreads that follows stage_args(slot)
-        const StepArgs<float> &n = s_step[slot].a;
-        if (tid < 32) s_al[slot][0][tid] = tid < n.R ? n.al_out[tid] : (uint8_t)0;
-        else if (tid < 64) s_al[slot][1][tid - 32] = tid - 32 < n.R ? n.al_in[tid - 32] : (uint8_t)0;
-    };
     stage_args(0, 0);
-    __syncthreads();
-    stage_alleles(0);
     __syncthreads();
 
     float inv = 1.f;
     for (uint32_t s = 0; s < w.n_steps; ++s) {
         const uint32_t slot = s & 1u;
         const StepArgs<float> &a = s_step[slot].a;
-        const uint8_t *al_out = s_al[slot][0], *al_in = s_al[slot][1];
+        const uint8_t *al_out = s_step[slot].al_out, *al_in = s_step[slot].al_in;
         if (s + 1 < w.n_steps) stage_args(s + 1, slot ^ 1u);      // visible after the __syncthreads before the barrier
         if (s == 0) inv = (float)(1.0 / *a.in_scale);
         float warp_sum = 0.f;
@@ -348,7 +365,6 @@ wave_kernel(const WaveArgs w) {
         }
         if (lane == 0) s_sum[warp] = warp_sum;
         __syncthreads();
-        if (s + 1 < w.n_steps) stage_alleles(slot ^ 1u);          // next step's arguments are in place since the barrier above
         if (FWD) {
             const uint32_t nA = a.nA_out;
             float *dst = w.w_partial + s_step[slot].w_off + (uint64_t)blockIdx.x * nA * nA;
@@ -359,27 +375,14 @@ wave_kernel(const WaveArgs w) {
                 dst[p] = q;
             }
         }
-        float *slots = w.sum_partial + (s & 1u) * gridDim.x;
+        float ts = 0.f;
         if (tid == 0) {
-            float ts = 0.f;
 #pragma unroll
             for (int k = 0; k < kWarpKernelWarps; ++k) ts += s_sum[k];
-            slots[blockIdx.x] = ts;
         }
-        wave_barrier(w.barrier, (s + 1) * gridDim.x);
-        // the column sum, identically in every CTA (warp 0: lane l takes slots l, l+32, ..., then a butterfly)
-        if (warp == 0) {
-            double acc = 0.0;
-            for (uint32_t k = lane; k < gridDim.x; k += 32) acc += (double)__ldcg(slots + k);
-#pragma unroll
-            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) {
-                s_inv = (float)(1.0 / acc);
-                if (blockIdx.x == 0) *a.out_scale = acc;
-            }
-        }
-        __syncthreads();
-        inv = s_inv;
+        const double total = wave_barrier_sum(w.barrier, s, ts, &s_total);
+        if (blockIdx.x == 0 && tid == 0) *a.out_scale = total;
+        inv = (float)(1.0 / total);
     }
 }
 
