@@ -460,6 +460,7 @@ struct Engine {
         GG_TMA(4, 1, 1, false, 8, false) GG_TMA(4, 2, 1, false, 8, false) GG_TMA(4, 4, 1, false, 8, false) GG_TMA(4, 8, 1, false, 8, false)
         GG_TMA(4, 16, 1, false, 8, false) GG_TMA(4, 32, 1, false, 8, false) GG_TMA(4, 32, 1, false, 16, false)
         GG_TMA(4, 16, 1, false, 8, true) GG_TMA(4, 32, 1, false, 8, true) GG_TMA(4, 32, 1, false, 16, true)
+        GG_TMA(4, 16, 2, false, 8, false) GG_TMA(4, 16, 2, false, 8, true)
         GG_TMA(4, 32, 1, true, 0, false) GG_TMA(4, 32, 2, true, 0, false) GG_TMA(4, 32, 4, true, 0, false)
         // float2 rows (R % 4 == 2, e.g. 94 haplotypes): panels of 34..256
         GG_TMA(2, 32, 1, false, 8, false) GG_TMA(2, 32, 1, false, 16, false) GG_TMA(2, 32, 1, false, 8, true) GG_TMA(2, 32, 1, false, 16, true)
@@ -471,8 +472,14 @@ struct Engine {
 
     static bool try_launch_tma(gg_hmm *h, const StepArgs<T> &a, const ColumnPlan &pco, bool fwd) {
         if (sizeof(T) != 4 || h->kernel_variant == 1 || a.in == nullptr) return false;
-        const int V = h->shape.V, NS = h->shape.NS;
+        const int V = h->shape.V;
+        int NS = h->shape.NS;
+        uint32_t G = a.G;
         if (V < 2 || a.R > 512) return false;
+        // rows of 17..32 vectors (R = 68..128 for float4): two rows per warp (16 lanes x 2 vectors each) instead of one
+        // row on 17..32 of 32 lanes: the per-row bookkeeping and the shuffle reduction are shared by two rows
+        static const int half_rows_env = [] { const char *e = std::getenv("GG_TMA_HALFROWS"); return e ? std::atoi(e) : 0; }();
+        if (V == 4 && G == 32 && NS == 1 && a.R <= 128 && (half_rows_env & (fwd ? 2 : 1))) { G = 16; NS = 2; }
         configure_once(h->device, 1, [] {
             for (int vv : {2, 4})
                 for (uint32_t g = 1; g <= 32; g <<= 1)
@@ -484,14 +491,14 @@ struct Engine {
                                         if (const void *kk = tma_kernel(f, vv, g, ns, mt, cwt, tw))
                                             GG_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
         });
-        const uint32_t rpi = 32 / a.G;
+        const uint32_t rpi = 32 / G;
         const uint32_t nred = fwd ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
         const uint32_t ncls = pco.n_alleles + 1;
         // geometry search.  Whole block = one tile (R <= 128): two CTAs of 8 consumer warps per SM when the column's
         // footprint fits twice, else one CTA of 16 (same warp count, deeper ring), else one of 8.  Larger R: row tiles
         // of <= ~40 KB, most consumer warps first, >= 3 stages.
         // both blocks of a two-block reduce set held in stages (where that kernel variant is compiled)
-        const bool two_ok = nred == 2 && a.R <= 128 && tma_kernel(fwd, V, a.G, NS, false, 8, true) != nullptr;
+        const bool two_ok = nred == 2 && a.R <= 128 && tma_kernel(fwd, V, G, NS, false, 8, true) != nullptr;
         struct Pick { uint32_t cw, tr, stages, ctas; int cwt; TmaGeom L; bool ok; } pick{};
         auto fit = [&](uint32_t cw, uint32_t tr, uint32_t lo, uint32_t hi, size_t cap, uint32_t &stages, TmaGeom &L) {
             for (stages = hi; stages >= lo; --stages) {
@@ -500,14 +507,14 @@ struct Engine {
             }
             return false;
         };
-        if (a.R <= 128 && tma_kernel(fwd, V, a.G, NS, false, 8, false)) {
+        if (a.R <= 128 && tma_kernel(fwd, V, G, NS, false, 8, false)) {
             uint32_t st; TmaGeom L;
             if (h->kernel_variant != 2 && fit(8, a.R, 3, 4, kMaxDynSmemTma2, st, L)) pick = {8, a.R, st, 2, 8, L, true};
-            else if (tma_kernel(fwd, V, a.G, NS, false, 16, false) && h->kernel_variant != 3 &&
+            else if (tma_kernel(fwd, V, G, NS, false, 16, false) && h->kernel_variant != 3 &&
                      fit(16, a.R, 3, kTmaMaxStages, kMaxDynSmemTma, st, L)) pick = {16, a.R, st, 1, 16, L, true};
             else if (fit(8, a.R, 3, kTmaMaxStages, kMaxDynSmemTma, st, L)) pick = {8, a.R, st, 1, 8, L, true};
         }
-        if (!pick.ok && a.G == 32) {
+        if (!pick.ok && G == 32) {
             for (uint32_t cw : {8u, 4u, 2u}) {
                 const uint32_t ngrp = cw * rpi;
                 uint32_t tr_max = std::min<uint32_t>(a.R, (40u * 1024u) / (a.R * 4u));
@@ -522,7 +529,7 @@ struct Engine {
             }
         }
         if (!pick.ok) return false;
-        const void *k = tma_kernel(fwd, V, a.G, NS, pick.cwt == 0, pick.cwt, two_ok && pick.cwt != 0);
+        const void *k = tma_kernel(fwd, V, G, NS, pick.cwt == 0, pick.cwt, two_ok && pick.cwt != 0);
         if (!k) return false;
         const int threads = 32 * (1 + (int)pick.cw);
         auto key = std::make_tuple(k, threads, (size_t)pick.L.total);

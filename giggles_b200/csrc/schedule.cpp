@@ -18,8 +18,10 @@ inline uint64_t up(uint64_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 // the quadratic last resort.  `cost` = bytes of backward columns produced while processing the range.
 struct Node {
     uint32_t lo = 0, hi = 0, depth = 1;
-    enum Kind : uint8_t { LEAF, SPLIT, QUAD } kind = LEAF;
+    enum Kind : uint8_t { LEAF, SPLIT, QUAD, EXACT } kind = LEAF;
     double cost = 0;
+    uint64_t avail = 0;      // EXACT: bytes the range may use beside its (resident) last backward column
+    bool virt = false;       // EXACT: the last backward column is the all-ones column and is re-created where needed
     std::vector<uint32_t> ends;
     std::vector<Node> parts;
 };
@@ -165,6 +167,18 @@ struct Builder {
             return true;
         }
         if (lo == hi) return false;
+        if (exact_eligible(lo, hi, avail)) {
+            try {
+                const XVal x = exact(lo, hi, avail, false);
+                if (x.p == -2) return false;
+                out.kind = Node::EXACT;
+                out.cost = x.cost;
+                out.avail = avail;
+                return true;
+            } catch (const ExactOverflow &) {
+                xmemo.clear();
+            }
+        }
         const uint64_t roll = roll_need(lo, hi);
         const uint32_t n = hi - lo + 1;
         const double mean_col = span_bytes(lo, hi) / n;
@@ -253,6 +267,86 @@ struct Builder {
         return false;
     }
 
+    // ------------------------------------------------------------------ exact planner (few, huge columns)
+    // Ranges of a few dozen columns of which only a handful fit (2^20 bipartitions at R = 88: 33 GB per column, five
+    // in HBM) are planned by exhaustive recursion instead of the heuristics above:
+    //   T(lo, hi, avail) = bytes(lo..hi-1)                                            if the range is a leaf
+    //                    = min_p  bytes(p..hi-1) + T(lo, p, avail - col_p) + T(p+1, hi, avail)
+    // i.e. sweep from beta_hi down to column p, keep beta_p, do the left part (whose own sweep carries on from
+    // beta_p: several checkpoints per sweep come out as left-nested splits), drop beta_p, do the right part.  The
+    // sweep alternates between a temporary and the destination itself (an output two steps before the last is dead
+    // by the time the last is written); the temporary is the alpha buffer the next forward step will write, idle
+    // while backward columns are being recomputed, so a sweep costs no room beyond its destination.  `virt`: the
+    // range ends at the chain's last column, whose beta is all ones: instead of keeping it resident from the first
+    // step of the sweep to the leaf of the last part, every use re-creates it (one write-only launch, costed at half
+    // a step) — with five columns of room that is the difference between no spare checkpoint and one.
+    struct XKey {
+        uint32_t lo, hi; uint64_t avail; bool virt;
+        bool operator<(const XKey &o) const {
+            if (lo != o.lo) return lo < o.lo;
+            if (hi != o.hi) return hi < o.hi;
+            if (avail != o.avail) return avail < o.avail;
+            return virt < o.virt;
+        }
+    };
+    struct XVal { double cost; int64_t p; };       // p = -1: leaf, -2: infeasible
+    mutable std::map<XKey, XVal> xmemo;
+    static constexpr uint32_t kExactMaxCols = 64;
+    static constexpr size_t kExactMaxStates = 400000;   // memo entries; beyond that the heuristics take over
+    struct ExactOverflow {};
+
+    bool exact_eligible(uint32_t lo, uint32_t hi, uint64_t avail) const {
+        if (hi - lo + 1 > kExactMaxCols) return false;
+        uint64_t maxcol = 0;
+        for (uint32_t c = lo; c <= hi; ++c) maxcol = std::max(maxcol, up(colb[c]));
+        return maxcol > 0 && avail / maxcol < 6;      // beyond that the heuristics are within a few percent and O(n)
+    }
+    // temporaries of the sweep that produces [hi if virt,] hi-1 .. p with beta_p as the destination
+    void sweep_need(uint32_t p, uint32_t hi, bool virt, uint64_t &t1, uint64_t &t2, uint64_t &fg) const {
+        t1 = t2 = 0;
+        const uint64_t dst = up(colb[p]);
+        const uint32_t first = virt ? hi : hi - 1;          // produced columns first, first-1, .., p
+        for (uint32_t c = first;; --c) {
+            const uint32_t k = c - p;                       // steps before the last one
+            const uint64_t b = up(colb[c]);
+            if (k & 1u) t1 = std::max(t1, b);
+            else if (k >= 2 && b > dst) t2 = std::max(t2, b);
+            if (c == p) break;
+        }
+        uint64_t maxfg = 0;
+        for (uint32_t c = p; c <= hi; ++c) maxfg = std::max(maxfg, up(fgb[c]));
+        fg = 2 * maxfg;
+    }
+    XVal exact(uint32_t lo, uint32_t hi, uint64_t avail, bool virt) const {
+        const XKey key{lo, hi, avail, virt};
+        auto it = xmemo.find(key);
+        if (it != xmemo.end()) return it->second;
+        if (xmemo.size() > kExactMaxStates) throw ExactOverflow{};
+        XVal best{1e300, -2};
+        const double init_cost = virt ? 0.5 * (double)up(colb[hi]) : 0.0;
+        const uint64_t own = virt ? up(colb[hi]) : 0;
+        if (leaf_need(lo, hi) + own <= avail) {
+            best = XVal{(hi > lo ? span_bytes(lo, hi - 1) : 0.0) + init_cost, -1};
+        } else if (hi > lo) {
+            for (uint32_t p = lo; p < hi; ++p) {
+                uint64_t t1, t2, fg;
+                sweep_need(p, hi, virt, t1, t2, fg);
+                const uint64_t ck = up(colb[p]);
+                if (ck + t2 + fg > avail) continue;       // t1 lives in the idle alpha buffer (see run_exact)
+                const double sweep = span_bytes(p, hi - 1) + init_cost;
+                if (sweep >= best.cost) continue;
+                const XVal l = exact(lo, p, avail - ck, false);
+                if (l.p == -2 || sweep + l.cost >= best.cost) continue;
+                const XVal r = exact(p + 1, hi, avail, virt);
+                if (r.p == -2) continue;
+                const double c = sweep + l.cost + r.cost;
+                if (c < best.cost) best = XVal{c, (int64_t)p};
+            }
+        }
+        xmemo[key] = best;
+        return best;
+    }
+
     // ------------------------------------------------------------------ emission
     void emit(uint32_t lo, uint32_t hi, uint64_t region) {
         Op o{};
@@ -274,10 +368,21 @@ struct Builder {
         ++s.n_fwd;
     }
 
-    void leaf(uint32_t lo, uint32_t hi, uint64_t beta_hi) {
+    void bwd_init(uint32_t c, uint64_t out_off, uint64_t fg_out) {
+        Op o{};
+        o.kind = OP_BWD_INIT; o.c = c; o.out_off = out_off; o.fg_out_off = fg_out;
+        s.ops.push_back(o);
+        ++s.n_bwd;
+    }
+
+    void leaf(uint32_t lo, uint32_t hi, uint64_t beta_hi, bool virt = false) {
         const uint64_t mark = top;
         const uint64_t fg = alloc(pfg[hi + 1] - pfg[lo]);
         emit(lo, hi, fg);
+        if (virt) {
+            beta_hi = alloc(colb[hi]);
+            bwd_init(hi, beta_hi, fg + (pfg[hi] - pfg[lo]));
+        }
         std::vector<uint64_t> offs(hi - lo + 1);
         offs[hi - lo] = beta_hi;
         for (uint32_t c = hi; c > lo; --c) {
@@ -288,9 +393,58 @@ struct Builder {
         top = mark;
     }
 
+    // emits the plan exact() found (its argmin is re-read from the memo)
+    void run_exact(uint32_t lo, uint32_t hi, uint64_t avail, bool virt, uint64_t beta_hi, uint32_t depth) {
+        max_depth = std::max(max_depth, depth);
+        const XVal x = exact(lo, hi, avail, virt);
+        if (x.p == -2) throw std::runtime_error("state budget too small for this problem (exact plan lost)");
+        if (x.p == -1) {
+            leaf(lo, hi, beta_hi, virt);
+            return;
+        }
+        max_depth = std::max(max_depth, depth + 1);
+        const uint32_t p = (uint32_t)x.p;
+        const uint64_t mark0 = top;
+        const uint64_t ck = alloc(colb[p]);
+        const uint64_t mark1 = top;
+        uint64_t t1, t2, fgn;
+        sweep_need(p, hi, virt, t1, t2, fgn);
+        // every forward column before lo is done and alpha_{lo-1} sits in alpha[(lo+1)&1]: the other alpha buffer (the
+        // one forward step lo will write) is idle until then and serves as the sweep's temporary
+        const uint64_t T1 = alpha[lo & 1], T2 = t2 ? alloc(t2) : 0;
+        uint64_t fbuf[2];
+        fbuf[0] = alloc(fgn / 2); fbuf[1] = alloc(fgn / 2);
+        auto buf_of = [&](uint32_t c) {
+            const uint32_t k = c - p;
+            if (k == 0) return ck;
+            if (k & 1u) return T1;
+            return up(colb[c]) <= up(colb[p]) ? ck : T2;
+        };
+        emit(hi, hi, fbuf[hi & 1]);
+        uint64_t cur = beta_hi;
+        if (virt) {
+            cur = buf_of(hi);
+            bwd_init(hi, cur, fbuf[hi & 1]);
+        }
+        for (uint32_t c = hi; c > p; --c) {
+            emit(c - 1, c - 1, fbuf[(c - 1) & 1]);
+            const uint64_t dst = buf_of(c - 1);
+            bwd(c - 1, cur, dst, fbuf[c & 1], fbuf[(c - 1) & 1]);
+            cur = dst;
+        }
+        top = mark1;
+        run_exact(lo, p, avail - up(colb[p]), false, ck, depth + 1);
+        top = mark0;
+        run_exact(p + 1, hi, avail, virt, beta_hi, depth + 1);
+    }
+
     void run(const Node &nd, uint64_t beta_hi) {
         max_depth = std::max(max_depth, nd.depth);
         const uint32_t lo = nd.lo, hi = nd.hi;
+        if (nd.kind == Node::EXACT) {
+            run_exact(lo, hi, nd.avail, nd.virt, beta_hi, nd.depth);
+            return;
+        }
         if (nd.kind == Node::LEAF) {
             leaf(lo, hi, beta_hi);
             return;
@@ -369,6 +523,30 @@ void build_schedule(const std::vector<uint64_t> &colb, const std::vector<uint64_
     for (uint64_t x : colb) maxcol = std::max(maxcol, x);
     b.alpha[0] = b.alloc(maxcol);
     b.alpha[1] = b.alloc(maxcol);
+    // few, huge columns: is the chain cheaper when its last (all-ones) backward column is re-created on demand
+    // instead of staying resident?  (see the exact planner)
+    if (C > 1 && b.exact_eligible(0, C - 1, budget > b.top ? budget - b.top : 0) && budget > b.top) {
+        const uint64_t avail_v = budget - b.top;
+        const uint64_t res = up(colb[C - 1]) + up(fgb[C - 1]);
+        bool use_virt = false;
+        try {
+            const auto xv = b.exact(0, C - 1, avail_v, true);
+            double cost_r = 1e300;
+            if (avail_v > res) {
+                const auto xr = b.exact(0, C - 1, avail_v - res, false);
+                if (xr.p != -2) cost_r = xr.cost + 0.5 * (double)up(colb[C - 1]);
+            }
+            use_virt = xv.p != -2 && xv.cost < cost_r;
+        } catch (const Builder::ExactOverflow &) {
+            b.xmemo.clear();
+        }
+        if (use_virt) {
+            b.run_exact(0, C - 1, avail_v, true, 0, 1);
+            out.arena_bytes = b.high;
+            out.levels = b.max_depth;
+            return;
+        }
+    }
     const uint64_t beta_last = b.alloc(colb[C - 1]);
     const uint64_t fg_last = b.alloc(fgb[C - 1]);
     b.emit(C - 1, C - 1, fg_last);

@@ -218,6 +218,26 @@ def test_checkpoint_schedule_does_not_change_results():
     assert max(seen_levels) >= 2
 
 
+@pytest.mark.parametrize("n_haps,slots", [(12, 3.3), (12, 1.3), (88, 3.3), (88, 2.3), (10, 3.3)])
+def test_exact_plan_for_few_huge_columns_does_not_change_results(n_haps, slots):
+    # room for alpha x 2 and `slots` of the largest column: the exact planner (nested checkpoints, idle alpha buffer
+    # as the sweep's temporary, all-ones last column re-created on demand) takes over — the configs[3] regime in
+    # miniature.  Same bits as the everything-fits schedule.
+    from giggles_b200 import fullscale as fs
+    p = make_problem(40, n_haps, coverage=6, max_coverage=6, read_len_mean=2500, seed=11, window=True)
+    cb, fb = fs.column_bytes(p.untagged_per_column(), n_haps, n_alleles=p.n_alleles)
+    budget = int((2 + slots) * int(cb.max()) + 4 * int(fb.max()) + 8192)
+    dry = capi.schedule_dry_run(cb, fb, budget)
+    assert dry["levels"] >= 3 and dry["n_bwd"] > 1.5 * p.n_columns      # deep recompute, several re-created last columns
+    base = capi.hmm_run(p, device=0).values
+    h = capi.Hmm(p, device=0, budget=budget)
+    h.sweep()
+    st = h.stats()
+    assert st["state_bytes_reserved"] <= budget and st["checkpoint_levels"] >= 3
+    assert np.array_equal(h.fetch().values, base)
+    h.close()
+
+
 def test_runs_are_deterministic():
     p = make_problem(40, 88, coverage=6, max_coverage=6, read_len_mean=1500, seed=9, window=True)
     a = capi.hmm_run(p, device=0).values

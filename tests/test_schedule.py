@@ -47,14 +47,38 @@ def test_single_and_empty():
     assert capi.schedule_dry_run([], [], 1 << 20)["n_fwd"] == 0
 
 
-def test_columns_of_a_fifth_of_hbm_use_the_quadratic_fallback():
-    # configs[3] with R = 88: one column is 33 GB; only two rolling backward columns fit beside alpha and the last beta
+def test_columns_of_a_fifth_of_hbm_get_an_exact_plan():
+    # configs[3] with R = 88: one column is 33 GB, five fit: alpha x 2 and three backward columns.  Round 1 recomputed
+    # the backward chain for every forward column (1 + 8*7/2 = 29 launches for 8 columns).  The exact planner nests
+    # checkpoints, uses the idle alpha buffer as the sweep's temporary and re-creates the all-ones last column instead
+    # of keeping it resident: 13 launches for 8 columns, ~4.1 per column for 64.
     col, fg = 33_235_664_896, 50_331_648
     r = capi.schedule_dry_run([col] * 8, [fg] * 8, 171_000_000_000)
-    assert r["n_fwd"] == 8 and r["n_bwd"] == 1 + 8 * 7 // 2 and r["arena_bytes"] <= 171_000_000_000
+    assert r["n_fwd"] == 8 and r["n_bwd"] <= 13 and r["arena_bytes"] <= 171_000_000_000
     assert r["levels"] >= 2            # a recomputing schedule never reports "everything fitted"
+    r = capi.schedule_dry_run([col] * 64, [fg] * 64, 171_000_000_000)
+    assert r["n_fwd"] == 64 and r["n_bwd"] <= 4.2 * 64 and r["bwd_col_bytes"] <= 4.1 * 63 * col
+    # alpha x 2 + ONE backward column still works (the chain is recomputed from the re-created last column for every
+    # forward column, alternating between that slot and the idle alpha buffer); less than that does not
+    r1 = capi.schedule_dry_run([col] * 8, [fg] * 8, 110_000_000_000)
+    assert r1["n_fwd"] == 8 and r1["arena_bytes"] <= 110_000_000_000
     with pytest.raises(capi.GGError):
-        capi.schedule_dry_run([col] * 8, [fg] * 8, 140_000_000_000)
+        capi.schedule_dry_run([col] * 8, [fg] * 8, 90_000_000_000)
+    # four columns of room: still a plan (leaves of two columns under one nested checkpoint)
+    r4 = capi.schedule_dry_run([col] * 8, [fg] * 8, 140_000_000_000)
+    assert r4["n_fwd"] == 8 and 13 < r4["n_bwd"] <= r1["n_bwd"]
+    # mixed sizes: the small columns become the checkpoints
+    cb = [col, col // 2, col, col, col // 4, col, col, col // 2, col, col, col, col]
+    rm = capi.schedule_dry_run(cb, [fg] * len(cb), 171_000_000_000)
+    assert rm["n_fwd"] == len(cb) and rm["n_bwd"] <= 2.5 * len(cb)
+
+
+def test_long_ranges_of_huge_columns_fall_back_to_the_heuristics():
+    # beyond 64 columns the exhaustive recursion is not attempted; the heuristic planner (and, when only two rolling
+    # columns fit, the quadratic recompute) still produce a valid schedule
+    col, fg = 33_235_664_896, 50_331_648
+    r = capi.schedule_dry_run([col] * 80, [fg] * 80, 171_000_000_000)
+    assert r["n_fwd"] == 80 and r["arena_bytes"] <= 171_000_000_000
 
 
 def test_full_length_config2_recompute_bound():
