@@ -28,6 +28,7 @@
 #include "../../include/giggles_b200.h"
 #include "hmm_kernels.cuh"
 #include "hmm_tma_kernel.cuh"
+#include "hmm_wide_kernel.cuh"
 #include "hmm_chain_kernel.cuh"
 #include "hmm_warp_kernel.cuh"
 #include "hmm_wave_kernel.cuh"
@@ -206,7 +207,7 @@ struct gg_hmm {
     Schedule sched;
     bool fp64 = false;
     bool shared_arena = false;   // GG_OPT_SHARED_ARENA: the state arena is borrowed per sweep
-    int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined, never two CTAs per SM, 3 = pipelined, never 16 consumer warps, 4 = no chain kernel, 5 = no warp-per-block kernel (nor wave runs), 7 = no wave runs (small panels column by column)
+    int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined, never two CTAs per SM, 3 = pipelined, never 16 consumer warps, 4 = no chain kernel, 5 = no warp-per-block kernel (nor wave runs), 7 = no wave runs (small panels column by column), 8 = no wide-panel kernel (R > 128 on the row-tiled pipelined kernel)
     int device = 0;
     int num_sms = 0;
     size_t elem = 4;
@@ -388,6 +389,18 @@ struct Engine {
         const uint32_t R = h->plan.n_haps;
         const ColumnPlan &pco = h->plan.cols[op.c];
         const StepArgs<T> a = make_args(h, op, fwd, init);
+        if (init) {
+            // the all-ones last backward column: a fill (init_kernel, hmm_kernels.cuh)
+            const uint64_t nb = (uint64_t)1 << pco.u;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(nb, (uint64_t)h->num_sms * 8);
+            const int V = h->shape.V;
+            if (V == 4) { if constexpr (sizeof(T) == 4) init_kernel<T, 4><<<grid, 256, 0, h->stream>>>(a); }
+            else if (V == 2) init_kernel<T, 2><<<grid, 256, 0, h->stream>>>(a);
+            else init_kernel<T, 1><<<grid, 256, 0, h->stream>>>(a);
+            GG_CUDA(cudaGetLastError());
+            ++h->stats.n_launches;
+            return;
+        }
         if (try_launch_warp(h, a, pco, fwd)) return;
         if (try_launch_tma(h, a, pco, fwd)) return;
         const uint32_t rpi = 32 / h->shape.G;
@@ -453,6 +466,45 @@ struct Engine {
         return true;
     }
 
+    // Wide panels (hmm_wide_kernel.cuh): fp32, R % 4 == 0, 128 < R <= 512, reduce sets of one or two blocks.
+    static bool try_launch_wide(gg_hmm *h, const StepArgs<T> &a, const ColumnPlan &pco, bool fwd, uint32_t nred) {
+        const bool two = nred == 2;
+        const void *k = fwd ? (two ? (const void *)wide_step_kernel<true, true> : (const void *)wide_step_kernel<true, false>)
+                            : (two ? (const void *)wide_step_kernel<false, true> : (const void *)wide_step_kernel<false, false>);
+        configure_once(h->device, 5, [] {
+            for (const void *kk : {(const void *)wide_step_kernel<true, true>, (const void *)wide_step_kernel<true, false>,
+                                   (const void *)wide_step_kernel<false, true>, (const void *)wide_step_kernel<false, false>})
+                GG_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma));
+        });
+        const uint32_t ncls = pco.n_alleles + 1;
+        const uint32_t cw = (a.R + 63u) / 64u;
+        const uint32_t nload = nred + (fwd ? 1u : 0u);
+        // most row interleaves (consumer warps) first, then the deepest ring of ~32 KB tiles that fits
+        struct { uint32_t rh, tr, stages; WideGeom L; bool ok; } pick{};
+        for (uint32_t rh : {2u, 1u}) {
+            if (cw * rh > kWideMaxWarps) continue;
+            const uint32_t tr_max = std::max<uint32_t>(2u, std::min<uint32_t>(a.R, (32u * 1024u) / (a.R * 4u)) & ~1u);
+            for (uint32_t tr : {tr_max, std::max<uint32_t>(2u, (tr_max / 2u) & ~1u)}) {
+                for (uint32_t st = std::min<uint32_t>(kTmaMaxStages, 2u * nload + 2u); st >= nload + 1u && !pick.ok; --st) {
+                    const WideGeom L = wide_geom(a.R, tr, st, cw, rh, ncls, fwd);
+                    if (L.total <= kMaxDynSmemTma) pick = {rh, tr, st, L, true};
+                }
+                if (pick.ok) break;
+            }
+            if (pick.ok) break;
+        }
+        if (!pick.ok) return false;
+        const uint64_t n_items = (uint64_t)1 << pco.u;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)h->num_sms);
+        StepArgs<float> af;
+        std::memcpy(&af, &a, sizeof(af));
+        uint32_t ns = pick.stages, tr = pick.tr, cwv = cw, rhv = pick.rh;
+        void *params[] = {(void *)&af, (void *)&ns, (void *)&tr, (void *)&cwv, (void *)&rhv};
+        GG_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(32 * (1 + cw * pick.rh)), params, pick.L.total, h->stream));
+        ++h->stats.n_launches;
+        return true;
+    }
+
     // Pipelined bulk-copy kernel (hmm_tma_kernel.cuh): fp32, R % 4 == 0, R <= 512.
     static const void *tma_kernel(bool fwd, int V, uint32_t G, int NS, bool mt, int cwt, bool two) {
 #define GG_TMA(VV, GG, NN, MM, CC, TT) if (V == VV && G == GG && NS == NN && mt == MM && cwt == CC && two == TT) return fwd ? (const void *)step_tma_kernel<true, GG, NN, MM, CC, TT, VV> : (const void *)step_tma_kernel<false, GG, NN, MM, CC, TT, VV>;
@@ -494,6 +546,7 @@ struct Engine {
         const uint32_t rpi = 32 / G;
         const uint32_t nred = fwd ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
         const uint32_t ncls = pco.n_alleles + 1;
+        if (a.R > 128 && V == 4 && nred <= 2 && h->kernel_variant != 8 && try_launch_wide(h, a, pco, fwd, nred)) return true;
         // geometry search.  Whole block = one tile (R <= 128): two CTAs of 8 consumer warps per SM when the column's
         // footprint fits twice, else one CTA of 16 (same warp count, deeper ring), else one of 8.  Larger R: row tiles
         // of <= ~40 KB, most consumer warps first, >= 3 stages.

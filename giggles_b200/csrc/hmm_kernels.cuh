@@ -552,4 +552,70 @@ step_kernel(const StepArgs<T> a) {
     }
 }
 
+// The chain's last backward column: beta = 1 on every state whose two alleles are present (reference
+// src/genotypehmm.cpp:115-128 fills it with ones; the states with a missing allele carry no emission and are kept at
+// 0 as everywhere else), side sums of beta * E.  The values of every block are the same 0/1 pattern, only the side
+// record depends on b, so this is a pure fill: each thread keeps its column pattern in registers and streams rows.
+// A chain whose columns are tens of GB re-creates this column several times per sweep (schedule.cpp, exact planner)
+// — the generic step kernel took 16 ms for 33 GB (per-item latency), this one is write-bound.
+// row[R1] = F[a(R1)] * SG, col[R2] = G[a(R2)] * SF, total = SF * SG with SF = sum_j n_j F[j], SG = sum_j n_j G[j]
+// (n_j = haplotypes carrying allele j), summed in allele order: the same bits whatever the grid.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) init_kernel(const StepArgs<T> a) {
+    __shared__ uint8_t s_al[1024 + 8];
+    __shared__ uint32_t s_cnt[kMaxClasses];
+    const uint32_t R = a.R, NC = a.nA_out + 1, fgs = 2 * NC, RR = R * R;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t t = tid; t < R; t += blockDim.x) s_al[t] = a.al_out[t];
+    __syncthreads();
+    if (tid < NC) {
+        uint32_t n = 0;
+        for (uint32_t r = 0; r < R; ++r) n += s_al[r] == tid ? 1u : 0u;
+        s_cnt[tid] = n;
+    }
+    __syncthreads();
+    const uint32_t nvec = R / V;
+    const bool fast = nvec <= blockDim.x;
+    const uint32_t cchunk = fast ? tid % nvec : 0u, r0 = fast ? tid / nvec : 0u, rstep = fast ? blockDim.x / nvec : 1u;
+    T pat[V], zero[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        pat[v] = s_al[cchunk * V + v] != 0 ? T(1) : T(0);
+        zero[v] = T(0);
+    }
+    const uint64_t nb = (uint64_t)1 << a.u_out;
+    for (uint64_t b = blockIdx.x; b < nb; b += gridDim.x) {
+        T *blk = a.out + b * a.BS;
+        if (fast) {
+            if (r0 < rstep)
+                for (uint32_t R1 = r0; R1 < R; R1 += rstep)
+                    store_vec<T, V>(blk + (uint64_t)R1 * R + cchunk * V, s_al[R1] != 0 ? pat : zero);
+        } else {
+            for (uint32_t q = tid; q < R * nvec; q += blockDim.x) {
+                const uint32_t R1 = q / nvec, cc = q % nvec;
+                T o[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) o[v] = (s_al[R1] != 0 && s_al[cc * V + v] != 0) ? T(1) : T(0);
+                store_vec<T, V>(blk + (uint64_t)R1 * R + cc * V, o);
+            }
+        }
+        const T *fg = a.fg_out + b * fgs;
+        T SF = T(0), SG = T(0);
+        for (uint32_t j = 1; j < NC; ++j) {
+            SF += (T)s_cnt[j] * fg[j];
+            SG += (T)s_cnt[j] * fg[NC + j];
+        }
+        for (uint32_t t = tid; t < R; t += blockDim.x) {
+            blk[RR + t] = fg[s_al[t]] * SG;
+            blk[RR + R + t] = fg[NC + s_al[t]] * SF;
+        }
+        if (tid == 0) blk[RR + 2 * R] = SF * SG;
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        const double nv = (double)(R - s_cnt[0]);
+        *a.out_scale = nv * nv * (double)nb;
+    }
+}
+
+
 }  // namespace gg
