@@ -153,8 +153,8 @@ def main():
                          "full-length recompute; the others are side measurements of single windows (default budget)")
     ap.add_argument("--total-columns", type=int, default=1536, help="genome workload: variant sites over all 24 chains")
     ap.add_argument("--columns", type=int, default=None, help="side workloads: variant sites per window")
-    ap.add_argument("--max-coverage", type=int, default=15)
-    ap.add_argument("--haps", type=int, default=88)
+    ap.add_argument("--max-coverage", type=int, default=None, help="default: the workload's preset")
+    ap.add_argument("--haps", type=int, default=None, help="default: the workload's preset")
     ap.add_argument("--recompute", default="full-length", choices=["full-length", "default"],
                     help="genome workload: full-length = per-chain budgets that reproduce the 516k-column schedule's "
                          "backward bytes per column; default = the library's default budget (94 %% of free HBM)")
@@ -165,12 +165,14 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     presets = {"genome": (None, 15, 88), "config2": (256, 15, 88), "config1": (5000, 15, 10), "tagged": (20000, 15, 88),
-               "config4": (8, 20, 88), "config5": (48, 8, 400)}
+               "config4": (8, 20, 88), "config5": (24, 12, 400)}
     d_cols, d_cov, d_haps = presets[args.workload]
     if args.columns is None:
         args.columns = d_cols
-    if args.workload not in ("config2", "genome"):
-        args.max_coverage, args.haps = d_cov, d_haps
+    if args.max_coverage is None:
+        args.max_coverage = d_cov
+    if args.haps is None:
+        args.haps = d_haps
     genome = args.workload == "genome"
 
     rank = int(os.environ.get("RANK", "0"))

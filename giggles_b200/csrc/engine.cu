@@ -479,15 +479,20 @@ struct Engine {
         const uint32_t ncls = pco.n_alleles + 1;
         const uint32_t cw = (a.R + 63u) / 64u;
         const uint32_t nload = nred + (fwd ? 1u : 0u);
-        // most row interleaves (consumer warps) first, then the deepest ring of ~32 KB tiles that fits
+        // two row interleaves (twice the consumer warps) first; tiles of ~32 KB, then 3/4 and 1/2 of that; a ring that
+        // holds two tiles' worth of loads (2 x nload stages) or more, so that the next tile is in flight while this one
+        // is consumed; only then shallower rings
         struct { uint32_t rh, tr, stages; WideGeom L; bool ok; } pick{};
-        for (uint32_t rh : {2u, 1u}) {
-            if (cw * rh > kWideMaxWarps) continue;
-            const uint32_t tr_max = std::max<uint32_t>(2u, std::min<uint32_t>(a.R, (32u * 1024u) / (a.R * 4u)) & ~1u);
-            for (uint32_t tr : {tr_max, std::max<uint32_t>(2u, (tr_max / 2u) & ~1u)}) {
-                for (uint32_t st = std::min<uint32_t>(kTmaMaxStages, 2u * nload + 2u); st >= nload + 1u && !pick.ok; --st) {
-                    const WideGeom L = wide_geom(a.R, tr, st, cw, rh, ncls, fwd);
-                    if (L.total <= kMaxDynSmemTma) pick = {rh, tr, st, L, true};
+        const uint32_t tr_max = std::max<uint32_t>(2u, std::min<uint32_t>(a.R, (32u * 1024u) / (a.R * 4u)) & ~1u);
+        for (uint32_t min_st : {2u * nload, nload + 1u}) {
+            for (uint32_t rh : {2u, 1u}) {
+                if (cw * rh > kWideMaxWarps) continue;
+                for (uint32_t tr : {tr_max, std::max<uint32_t>(2u, (tr_max * 3u / 4u) & ~1u), std::max<uint32_t>(2u, (tr_max / 2u) & ~1u)}) {
+                    for (uint32_t st = std::min<uint32_t>(kTmaMaxStages, 3u * nload); st >= min_st && !pick.ok; --st) {
+                        const WideGeom L = wide_geom(a.R, tr, st, cw, rh, ncls, fwd);
+                        if (L.total <= kMaxDynSmemTma) pick = {rh, tr, st, L, true};
+                    }
+                    if (pick.ok) break;
                 }
                 if (pick.ok) break;
             }

@@ -6,8 +6,8 @@
 // beside the stages (configs[4]: forward step at 0.22 of the measured HBM peak).  Here a consumer warp owns 64
 // columns (16 float4; its two half-warps work on two rows at a time) for ALL rows of a block:
 //   * column sums and the posterior accumulators are private to one lane: the posterior scratch is one
-//     accumulator per (half-warp, allele class of the row, column) whatever the number of warps, and rows are
-//     visited in natural order (no class sorting, no parking);
+//     accumulator per (row interleave, allele class of the row, column) whatever the number of column groups, and
+//     rows are visited in natural order (no class sorting, no parking);
 //   * row sums become a 16-lane shuffle plus one fold over the column-owning warps per block;
 //   * one float4 of state per lane: ~60 registers, no spills.
 // The producer warp, the stage ring and the mbarrier protocol are those of step_tma_kernel with row tiles: a work
@@ -36,10 +36,10 @@ __host__ __device__ inline WideGeom wide_geom(uint32_t R, uint32_t TR, uint32_t 
     g.off_stage = o; o += n_stages * g.stage_bytes;
     g.off_meta = o; o += n_stages * (uint32_t)sizeof(TmaStageMeta);
     o = (o + 15u) & ~15u;
-    g.off_side = o; o += 2u * (2u * Rp + 4u) * 4u;              // side sums of the (reduced) input block, by item parity
-    g.off_fgo = o; o += 2u * 48u * 4u;                          // F/G of the output block, by item parity
-    g.off_q = o; o += fwd ? 2u * RH * ncls_out * Rp * 4u : 0u;  // posterior: [row interleave][half-warp][class][column]
-    g.off_rowpart = o; o += 2u * CW * Rp * 4u;                  // row sums per column group, by item parity
+    g.off_side = o; o += (2u * Rp + 4u) * 4u;                   // side sums of the (reduced) input block
+    g.off_fgo = o; o += 48u * 4u;                               // F/G of the output block
+    g.off_q = o; o += fwd ? RH * ncls_out * Rp * 4u : 0u;       // posterior: [row interleave][class of the row][column]
+    g.off_rowpart = o; o += CW * Rp * 4u;                       // row sums per column group
     g.off_colpart = o; o += RH * Rp * 4u;
     g.off_totred = o; o += 2u * kWideMaxWarps * 4u;
     g.off_al_o = o; o += Rp;
@@ -84,7 +84,7 @@ wide_step_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_
         s_al_i[t] = a.al_in[t];
     }
     if (FWD)
-        for (uint32_t t = tid; t < 2u * RH * NCo * Rp; t += blockDim.x) s_q[t] = 0.f;
+        for (uint32_t t = tid; t < RH * NCo * Rp; t += blockDim.x) s_q[t] = 0.f;
     __syncthreads();
 
     if (warp == 0) {
@@ -158,7 +158,7 @@ wide_step_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_
         a2o[v] = s_al_o[col + v];
         a2i[v] = s_al_i[col + v];
     }
-    float *q_base = s_q + (size_t)((rh * 2u + h) * NCo) * Rp + col;     // + class * Rp
+    float *q_base = s_q + (size_t)(rh * NCo) * Rp + col;     // + class * Rp
     float cta_sum = 0.f, sacc = 0.f;
     uint32_t seq = 0, par_item = 0;
 
@@ -166,9 +166,10 @@ wide_step_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_
         float kx[4], kx1[4], kr[4], kc[4], gout[4], colacc[4];
         float totv = 0.f;
         float *outp = nullptr;
-        float *s_side = reinterpret_cast<float *>(smem_raw + L.off_side) + par_item * (2u * Rp + 4u);
-        float *s_fgo = reinterpret_cast<float *>(smem_raw + L.off_fgo) + par_item * 48u;
-        float *rowpart = s_rowpart + par_item * CW * Rp;
+        // single buffers: the two barriers of the item epilogue separate their last readers from the next item's writers
+        float *s_side = reinterpret_cast<float *>(smem_raw + L.off_side);
+        float *s_fgo = reinterpret_cast<float *>(smem_raw + L.off_fgo);
+        float *rowpart = s_rowpart;
 
         for (uint32_t t = 0; t < n_tiles; ++t) {
             const uint32_t row0 = t * TR, rows = min(TR, R - row0);
@@ -192,7 +193,7 @@ wide_step_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_
             }
             if (t == 0) {
                 // the block's side sums (row, column, total of the reduced input) and F/G of the output block are kept
-                // for the later tiles; the buffers alternate between items, so one barrier per item suffices here
+                // for the later tiles
                 const float *sd0 = reinterpret_cast<const float *>(st0 + L.side_off);
                 const float *sd1 = reinterpret_cast<const float *>(st1 + L.side_off);
                 for (uint32_t q = ctid; q < 2 * R + 1; q += nct) s_side[q] = sd0[q] + (TWO ? sd1[q] : 0.f);
@@ -262,14 +263,25 @@ wide_step_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_
                     }
                     rs = fo * dot;
                 }
-                if (valid && cok) {
-                    *reinterpret_cast<float4 *>(outp + (uint64_t)R1 * R + col) = make_float4(o[0], o[1], o[2], o[3]);
-                    if (FWD) {
-                        const float4 b4 = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(stb) + eoff);
+                if (valid && cok) *reinterpret_cast<float4 *>(outp + (uint64_t)R1 * R + col) = make_float4(o[0], o[1], o[2], o[3]);
+                if (FWD) {
+                    // posterior: q[class of the row][column] += alpha * beta.  The two half-warps hold two rows of the
+                    // same columns: when the rows share a class the lower half adds both products, otherwise each half
+                    // adds its own — one accumulator array per row interleave, no two lanes on one address
+                    const float4 b4 = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(stb) + eoff);
+                    const bool live = valid && cok;
+                    float p0 = live ? o[0] * b4.x : 0.f, p1 = live ? o[1] * b4.y : 0.f;
+                    float p2 = live ? o[2] * b4.z : 0.f, p3 = live ? o[3] * b4.w : 0.f;
+                    const uint32_t cls_me = valid ? a1o : 0xffffffffu;
+                    const uint32_t cls_ot = __shfl_xor_sync(0xffffffffu, cls_me, 16);
+                    const float r0 = __shfl_xor_sync(0xffffffffu, p0, 16), r1 = __shfl_xor_sync(0xffffffffu, p1, 16);
+                    const float r2 = __shfl_xor_sync(0xffffffffu, p2, 16), r3 = __shfl_xor_sync(0xffffffffu, p3, 16);
+                    const bool same = cls_ot == cls_me;
+                    if (h == 0 && same) { p0 += r0; p1 += r1; p2 += r2; p3 += r3; }
+                    if (live && (h == 0 || !same)) {
                         float4 *qp = reinterpret_cast<float4 *>(q_base + (size_t)a1o * Rp);
                         float4 q4 = *qp;
-                        q4.x = fmaf(o[0], b4.x, q4.x); q4.y = fmaf(o[1], b4.y, q4.y);
-                        q4.z = fmaf(o[2], b4.z, q4.z); q4.w = fmaf(o[3], b4.w, q4.w);
+                        q4.x += p0; q4.y += p1; q4.z += p2; q4.w += p3;
                         *qp = q4;
                     }
                 }
@@ -331,7 +343,7 @@ wide_step_kernel(const StepArgs<float> a, const uint32_t n_stages, const uint32_
         for (uint32_t idx = ctid; idx < NCo * R; idx += nct) {
             const uint32_t cls = idx / R, t = idx % R;
             float v = 0.f;
-            for (uint32_t g = 0; g < 2u * RH; ++g) v += s_q[(size_t)(g * NCo + cls) * Rp + t];
+            for (uint32_t g = 0; g < RH; ++g) v += s_q[(size_t)(g * NCo + cls) * Rp + t];
             s_q[(size_t)cls * Rp + t] = v;
         }
         consumer_bar(nct);

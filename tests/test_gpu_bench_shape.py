@@ -44,6 +44,18 @@ SHAPES = [
                             read_len_sigma=0.5, window=True, seed=1104, **SOFT), 9, (0, 2)),       # float2 rows (R % 4 == 2)
     ("R128_u10_events", dict(n_columns=6, n_haps=128, region_bp=6 * 124, coverage=40, max_coverage=10, read_len_mean=400,
                              read_len_sigma=0.5, window=True, seed=1105, **SOFT), 9, (0, 2)),
+    # wide panels (hmm_wide_kernel.cuh: warps own columns; 8 = the row-tiled pipelined kernel instead): configs[4]'s
+    # 400 haplotypes with 3..16 alleles per site, more blocks than SMs, reads starting and ending inside the window
+    ("R400_u8_multiallelic_events", dict(n_columns=5, n_haps=400, region_bp=5 * 124, coverage=40, max_coverage=8,
+                                         read_len_mean=350, read_len_sigma=0.5, window=True, multiallelic_frac=1.0,
+                                         max_alleles=16, seed=1106, **SOFT), 8, (0, 8)),
+    ("R200_u9_multiallelic_mixed_tags", dict(n_columns=6, n_haps=200, region_bp=6 * 124, coverage=50, max_coverage=12,
+                                             read_len_mean=400, read_len_sigma=0.5, tags="mixed", window=True,
+                                             multiallelic_frac=0.5, max_alleles=8, missing_frac=0.02, seed=1107, **SOFT), 7, (0, 8)),
+    ("R132_u9_events", dict(n_columns=6, n_haps=132, region_bp=6 * 124, coverage=40, max_coverage=9, read_len_mean=400,
+                            read_len_sigma=0.5, window=True, seed=1108, **SOFT), 8, (0,)),          # 33 float4 per row: 3 column groups, the last one a single lane pair
+    ("R256_u8_events", dict(n_columns=5, n_haps=256, region_bp=5 * 124, coverage=40, max_coverage=8, read_len_mean=400,
+                            read_len_sigma=0.5, window=True, seed=1109, **SOFT), 7, (0,)),
 ]
 
 
