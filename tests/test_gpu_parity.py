@@ -219,7 +219,8 @@ def test_checkpoint_schedule_does_not_change_results():
 
 
 @pytest.mark.parametrize("n_haps,slots", [(12, 3.3), (12, 1.3), (88, 3.3), (88, 2.3), (10, 3.3)])
-def test_exact_plan_for_few_huge_columns_does_not_change_results(n_haps, slots):
+def test_exact_plan_for_few_huge_columns_does_not_change_results(n_haps, slots, monkeypatch):
+    monkeypatch.setenv("GG_EXACT_MIN_COL", "0")       # the planner reserves the recursion for columns >= 4 GiB
     # room for alpha x 2 and `slots` of the largest column: the exact planner (nested checkpoints, idle alpha buffer
     # as the sweep's temporary, all-ones last column re-created on demand) takes over — the configs[3] regime in
     # miniature.  Same bits as the everything-fits schedule.

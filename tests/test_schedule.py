@@ -67,6 +67,9 @@ def test_columns_of_a_fifth_of_hbm_get_an_exact_plan():
     # four columns of room: still a plan (leaves of two columns under one nested checkpoint)
     r4 = capi.schedule_dry_run([col] * 8, [fg] * 8, 140_000_000_000)
     assert r4["n_fwd"] == 8 and 13 < r4["n_bwd"] <= r1["n_bwd"]
+    # small columns under a budget of a few columns stay with the heuristics unless asked (planning time, schedule.cpp)
+    small = capi.schedule_dry_run([col >> 8] * 8, [fg >> 8] * 8, 171_000_000_000 >> 8)
+    assert small["n_fwd"] == 8 and small["n_bwd"] > 13
     # mixed sizes: the small columns become the checkpoints
     cb = [col, col // 2, col, col, col // 4, col, col, col // 2, col, col, col, col]
     rm = capi.schedule_dry_run(cb, [fg] * len(cb), 171_000_000_000)
