@@ -727,6 +727,12 @@ struct Engine {
     static const void *wave_kernel_ptr(bool fwd, int V, uint32_t G, uint32_t R) {
 #define GG_WV(VV, GG, RL) if (V == VV && G == GG && rl == RL) return fwd ? (const void *)wave_kernel<VV, GG, true, RL> : (const void *)wave_kernel<VV, GG, false, RL>;
         const uint32_t rl = (R % 2 == 0 && R <= 16) ? R : 0;
+        static const bool no_pair = std::getenv("GG_NO_PAIR_WAVE") != nullptr;      // A/B: thread-per-block path instead
+        if (rl && !no_pair) {
+#define GG_PW(RL) if (rl == RL) return fwd ? (const void *)pair_wave_kernel<RL, true> : (const void *)pair_wave_kernel<RL, false>;
+            GG_PW(2) GG_PW(4) GG_PW(6) GG_PW(8) GG_PW(10) GG_PW(12) GG_PW(14) GG_PW(16)
+#undef GG_PW
+        }
         GG_WV(2, 1, 2) GG_WV(4, 1, 4) GG_WV(2, 4, 6) GG_WV(4, 2, 8) GG_WV(2, 8, 10) GG_WV(4, 4, 12) GG_WV(2, 8, 14) GG_WV(4, 4, 16)
         GG_WV(2, 1, 0) GG_WV(2, 2, 0) GG_WV(2, 4, 0) GG_WV(2, 8, 0) GG_WV(2, 16, 0) GG_WV(4, 1, 0) GG_WV(4, 2, 0) GG_WV(4, 4, 0) GG_WV(4, 8, 0)
 #undef GG_WV
@@ -939,7 +945,8 @@ struct Engine {
             occ = std::min(occ, occ_b);
             if (occ < 1) throw CudaError(GG_ERR_CUDA, "wave kernel does not fit on an SM");
             const uint64_t max_items = (uint64_t)1 << pl.max_u;
-            h->wave_grid = (uint32_t)std::min<uint64_t>((uint64_t)h->num_sms * std::min(occ, GG_WAVE_MIN_CTAS),
+            const bool pair = pl.n_haps % 2 == 0 && pl.n_haps <= 16 && std::getenv("GG_NO_PAIR_WAVE") == nullptr;
+            h->wave_grid = (uint32_t)std::min<uint64_t>((uint64_t)h->num_sms * std::min(occ, pair ? GG_PAIR_CTAS : GG_WAVE_MIN_CTAS),
                                                        std::max<uint64_t>(1, (max_items + kWarpKernelWarps - 1) / kWarpKernelWarps));
         }
         const size_t o_wsteps = carve(h->wave_ops.size() * sizeof(WaveStep));

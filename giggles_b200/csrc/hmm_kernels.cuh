@@ -155,16 +155,14 @@ __host__ __device__ inline SmemLayout smem_layout(uint32_t R, uint32_t ngrp, uin
 // then has emission in [1, 4) whatever the reads say, and because the factors are powers of two the fp32 roundings
 // - hence the posteriors - are bit-identical to the unshifted tables wherever those did not underflow.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int PASS>
-__global__ void __launch_bounds__(256)
-emission_kernel(const ColDesc *__restrict__ cols, const uint8_t *__restrict__ em_side,
-                const double *__restrict__ em_prob, T *__restrict__ region, uint64_t prefix_lo, uint32_t lo,
-                double *__restrict__ emax) {
-    const uint32_t c = lo + blockIdx.y;
-    const ColDesc d = cols[c];
+// NAM: compile-time bound on the alleles of the column (2, 4, 8 or GG_MAX_ALLELES): the products live in registers,
+// so the loop over alleles must be unrolled, and unrolled to 16 a biallelic column spent 14 of 16 issue slots on
+// predicated-off multiplies (configs[0]: the two passes were 15 % of a sweep).
+template <typename T, int PASS, int NAM>
+__device__ __forceinline__ void emission_body(const ColDesc &d, const uint32_t c, const uint8_t *__restrict__ em_side,
+                                              const double *__restrict__ em_prob, T *__restrict__ fg, double *__restrict__ emax) {
     const uint32_t nA = d.n_alleles, NC = nA + 1;
     const uint64_t n2 = (uint64_t)2 << d.u;                      // (b, side) pairs; even, so lanes 2k / 2k+1 share b
-    T *fg = PASS == 1 ? region + (d.fg_prefix - prefix_lo) : nullptr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     int eM = 0;
@@ -177,9 +175,9 @@ emission_kernel(const ColDesc *__restrict__ cols, const uint8_t *__restrict__ em
         const uint64_t idx = base + lane;
         const bool active = idx < n2;
         const uint32_t side = (uint32_t)(idx & 1), b = (uint32_t)(idx >> 1);
-        double p[GG_MAX_ALLELES];
+        double p[NAM];
 #pragma unroll
-        for (int i = 0; i < GG_MAX_ALLELES; ++i) p[i] = 1.0;
+        for (int i = 0; i < NAM; ++i) p[i] = 1.0;
         if (active)
             for (uint32_t e = 0; e < d.em_count; ++e) {
                 const uint32_t sc = em_side[d.em_off + e];
@@ -187,14 +185,14 @@ emission_kernel(const ColDesc *__restrict__ cols, const uint8_t *__restrict__ em
                 if (s == side) {
                     const double *q = em_prob + d.em_prob_off + (uint64_t)e * nA;
 #pragma unroll
-                    for (int i = 0; i < GG_MAX_ALLELES; ++i)
+                    for (int i = 0; i < NAM; ++i)
                         if ((uint32_t)i < nA) p[i] *= q[i];
                 }
             }
         // only alleles some panel haplotype carries here can be the allele of a state (the others never reach the sweep)
         double mx = 0.0;
 #pragma unroll
-        for (int i = 0; i < GG_MAX_ALLELES; ++i)
+        for (int i = 0; i < NAM; ++i)
             if ((uint32_t)i < nA && ((d.present >> i) & 1u)) mx = fmax(mx, p[i]);
         const double other = __shfl_xor_sync(0xffffffffu, mx, 1);
         if (PASS == 0) {
@@ -206,7 +204,7 @@ emission_kernel(const ColDesc *__restrict__ cols, const uint8_t *__restrict__ em
             T *dst = fg + idx * NC;
             dst[0] = T(0);
 #pragma unroll
-            for (int i = 0; i < GG_MAX_ALLELES; ++i)
+            for (int i = 0; i < NAM; ++i)
                 if ((uint32_t)i < nA) dst[1 + i] = (T)ldexp(p[i], sh);
         }
     }
@@ -216,6 +214,20 @@ emission_kernel(const ColDesc *__restrict__ cols, const uint8_t *__restrict__ em
         if (lane == 0 && wmax > 0.0)
             atomicMax(reinterpret_cast<unsigned long long *>(emax + c), (unsigned long long)__double_as_longlong(wmax));
     }
+}
+
+template <typename T, int PASS>
+__global__ void __launch_bounds__(256)
+emission_kernel(const ColDesc *__restrict__ cols, const uint8_t *__restrict__ em_side,
+                const double *__restrict__ em_prob, T *__restrict__ region, uint64_t prefix_lo, uint32_t lo,
+                double *__restrict__ emax) {
+    const uint32_t c = lo + blockIdx.y;
+    const ColDesc d = cols[c];
+    T *fg = PASS == 1 ? region + (d.fg_prefix - prefix_lo) : nullptr;
+    if (d.n_alleles <= 2) emission_body<T, PASS, 2>(d, c, em_side, em_prob, fg, emax);
+    else if (d.n_alleles <= 4) emission_body<T, PASS, 4>(d, c, em_side, em_prob, fg, emax);
+    else if (d.n_alleles <= 8) emission_body<T, PASS, (GG_MAX_ALLELES < 8 ? GG_MAX_ALLELES : 8)>(d, c, em_side, em_prob, fg, emax);
+    else emission_body<T, PASS, GG_MAX_ALLELES>(d, c, em_side, em_prob, fg, emax);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -8,5 +8,5 @@ p = config1(n_columns=int(sys.argv[1]) if len(sys.argv) > 1 else 60)
 h = capi.Hmm(p, device=0)
 h.sweep(); h.sweep(True)
 s = h.stats()
-print({k: s[k] for k in ("n_columns", "state_columns", "max_untagged", "n_launches", "last_sweep_ms", "last_fwd_ms", "last_bwd_ms")})
+print({k: s[k] for k in ("n_columns", "state_columns", "max_untagged", "n_launches", "last_sweep_ms", "last_fwd_ms", "last_bwd_ms", "last_emit_ms")})
 h.close()
