@@ -68,3 +68,24 @@ def test_no_local_memory_spills_in_headline_kernels(functions):
         n = next(x for x in functions if re.search(pat, x))
         text = "\n".join(functions[n])
         assert "STL" not in text and "LDL" not in text, n
+
+
+def test_wide_panel_kernel_is_a_bulk_copy_pipeline_without_spills(functions):
+    # wide_step_kernel<FWD, TWO> (hmm_wide_kernel.cuh): the R > 128 path; one float4 of state per lane, so it must not spill
+    names = [n for n in functions if "wide_step_kernel" in n]
+    assert len(names) == 4
+    for n in names:
+        text = "\n".join(functions[n])
+        assert "UBLKCP" in text and "SYNCS" in text and "LDS.128" in text and "STG.E.128" in text, n
+        assert "STL" not in text and "LDL" not in text, n
+
+
+def test_small_panel_pair_kernel_does_not_spill_at_ten_haplotypes(functions):
+    # pair_wave_kernel<10, FWD>: configs[0]'s panel
+    names = [n for n in functions if re.search(r"pair_wave_kernelILi10E", n)]
+    assert len(names) == 2
+    for n in names:
+        text = "\n".join(functions[n])
+        assert "STL" not in text and "LDL" not in text, n
+        # the step arguments live in shared memory, so the column pointers are generic: LD.E.128 / ST.E.128
+        assert re.search(r"\bLDG?\.E\.128", text) and re.search(r"\bSTG?\.E\.128", text) and "SHFL.BFLY" in text, n
