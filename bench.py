@@ -437,7 +437,7 @@ def main():
                 break
             except Exception:
                 pass
-    kernel_name = "chain_kernel" if args.workload == "tagged" else ("pair_wave_kernel" if args.workload == "config1" else "step_tma_kernel")
+    kernel_name = "chain_kernel" if args.workload == "tagged" else ("pair_wave_kernel" if args.workload == "config1" else ("wide_step_kernel" if args.haps > 128 else "step_tma_kernel"))
     roofline = {
         "bound": "hbm", "kernel": f"step kernel, {dominant} ({kernel_name})", "achieved": ach, "peak": peak, "unit": "GB/s",
         "frac": ach / peak, "box_copy_GBps": box_copy_gbs, "frac_of_box_copy": (ach / box_copy_gbs if box_copy_gbs else None),

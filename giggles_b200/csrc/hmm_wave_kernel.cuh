@@ -409,6 +409,15 @@ __device__ __forceinline__ void pair_step(const StepArgs<float> &a, const uint8_
     const bool act = g8 < (uint32_t)NP;
     const uint32_t r = act ? 2u * g8 : 0u;
     const uint32_t BS = a.BS;
+    // the step record sits in shared memory, which hides the address space of the pointers in it from the compiler
+    // (generic LD/ST); say that they are global
+    const float *const p_in = a.in, *const p_beta = a.beta, *const p_fgo = a.fg_out, *const p_fgi = a.fg_in;
+    float *const p_out = a.out;
+    __builtin_assume(__isGlobal(p_in));
+    __builtin_assume(__isGlobal(p_out));
+    __builtin_assume(__isGlobal(p_fgo));
+    if (FWD) __builtin_assume(__isGlobal(p_beta));
+    if (!FWD) __builtin_assume(__isGlobal(p_fgi));
     const uint32_t NCo = a.nA_out + 1, NCi = a.nA_in + 1, fgs_o = 2 * NCo, fgs_i = 2 * NCi;
     const uint32_t nred = FWD ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
     const uint32_t n_bcast = FWD ? (a.u_out - a.n_sh) : a.n_free_left;
@@ -437,7 +446,7 @@ __device__ __forceinline__ void pair_step(const StepArgs<float> &a, const uint8_
         uint32_t blk_idx;
         if (FWD) blk_idx = want_beta ? (psh | (plo << a.n_sh)) : (sh_id ? psh : dev_pdep(psh, a.shared_mask));
         else blk_idx = psh;
-        const char *base = reinterpret_cast<const char *>((want_beta ? a.beta : a.in) + (uint64_t)blk_idx * BS);
+        const char *base = reinterpret_cast<const char *>((want_beta ? p_beta : p_in) + (uint64_t)blk_idx * BS);
         for (uint32_t l = pl; l < kLines; l += 4) prefetch_l1(base + l * 128);
     };
     for (uint32_t task = first_task; task < n_tasks; task += task_stride) {
@@ -454,8 +463,8 @@ __device__ __forceinline__ void pair_step(const StepArgs<float> &a, const uint8_
             b_out = (sh_id ? sh : dev_pdep(sh, a.shared_mask)) | (fr_id ? (lo << a.n_sh) : dev_pdep(lo, a.free_mask));
             b_in0 = sh;
         }
-        const float *fgo = a.fg_out + (uint64_t)b_out * fgs_o;
-        float *outp = a.out + (uint64_t)b_out * BS;
+        const float *fgo = p_fgo + (uint64_t)b_out * fgs_o;
+        float *outp = p_out + (uint64_t)b_out * BS;
         float gq[R], cb[R], colacc[R], gk0[R], x[2 * R];
         float totv = 0.f, rowv0 = 0.f, rowv1 = 0.f;
 #pragma unroll
@@ -468,7 +477,7 @@ __device__ __forceinline__ void pair_step(const StepArgs<float> &a, const uint8_
 #pragma unroll
         for (int e = 0; e < 2 * R; ++e) x[e] = 0.f;
         if (!FWD && nred == 1) {
-            const float *fgi = a.fg_in + (uint64_t)b_in0 * fgs_i;
+            const float *fgi = p_fgi + (uint64_t)b_in0 * fgs_i;
 #pragma unroll
             for (int j = 0; j < R; ++j) gk0[j] = fgi[NCi + ci[j]];
         }
@@ -477,7 +486,7 @@ __device__ __forceinline__ void pair_step(const StepArgs<float> &a, const uint8_
             for (uint32_t k = 0; k < nred; ++k) {
                 const uint64_t bk = FWD ? (uint64_t)(b_in0 | subm) : (uint64_t)(b_in0 | (k << a.n_sh));
                 subm = (subm - a.free_mask) & a.free_mask;
-                const float *blk = a.in + bk * BS;
+                const float *blk = p_in + bk * BS;
                 const float4 *src = reinterpret_cast<const float4 *>(blk + r * R);
                 float4 t4[NP];
 #pragma unroll
@@ -495,7 +504,7 @@ __device__ __forceinline__ void pair_step(const StepArgs<float> &a, const uint8_
                 float fk0 = 1.f, fk1 = 1.f;
                 const float *fgk = nullptr;
                 if (!FWD) {
-                    fgk = a.fg_in + bk * fgs_i;
+                    fgk = p_fgi + bk * fgs_i;
                     fk0 = fgk[ai[0]];
                     fk1 = fgk[ai[1]];
                 }
@@ -548,7 +557,7 @@ __device__ __forceinline__ void pair_step(const StepArgs<float> &a, const uint8_
             *reinterpret_cast<float2 *>(outp + o_row + r) = make_float2(rs[0], rs[1]);
         }
         if (FWD) {
-            const float4 *bsrc = reinterpret_cast<const float4 *>(a.beta + (uint64_t)b_out * BS + r * R);
+            const float4 *bsrc = reinterpret_cast<const float4 *>(p_beta + (uint64_t)b_out * BS + r * R);
 #pragma unroll
             for (int v = 0; v < NP; ++v) {
                 const float4 t = bsrc[v];

@@ -79,7 +79,8 @@ typedef struct gg_options {
                                          reuse the retired arena of that size (gg_arena_release() makes the next call ask again) */
     int32_t precision;                /* 0 = fp32 state with per-column scaling (production); 1 = fp64 state (validation) */
     int32_t kernel_variant;           /* 0 = auto; for A/B tests: 1 = generic step kernel only (no bulk-copy pipeline), 4 = no chain
-                                         kernel, 5 = no warp-per-block kernel, 7 = small panels column by column (no wave runs) */
+                                         kernel, 5 = no warp-per-block kernel, 7 = small panels column by column (no wave runs),
+                                         8 = wide panels (R > 128) on the row-tiled pipelined kernel instead of the column-owning one */
     uint32_t flags;                   /* GG_OPT_* */
 } gg_options;
 
