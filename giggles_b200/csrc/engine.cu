@@ -29,6 +29,7 @@
 #include "hmm_kernels.cuh"
 #include "hmm_tma_kernel.cuh"
 #include "hmm_wide_kernel.cuh"
+#include "hmm_colown_kernel.cuh"
 #include "hmm_chain_kernel.cuh"
 #include "hmm_warp_kernel.cuh"
 #include "hmm_wave_kernel.cuh"
@@ -207,7 +208,7 @@ struct gg_hmm {
     Schedule sched;
     bool fp64 = false;
     bool shared_arena = false;   // GG_OPT_SHARED_ARENA: the state arena is borrowed per sweep
-    int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined, never two CTAs per SM, 3 = pipelined, never 16 consumer warps, 4 = no chain kernel, 5 = no warp-per-block kernel (nor wave runs), 7 = no wave runs (small panels column by column), 8 = no wide-panel kernel (R > 128 on the row-tiled pipelined kernel)
+    int kernel_variant = 0;   // 0 = auto, 1 = generic step kernel only, 2 = pipelined, never two CTAs per SM, 3 = pipelined, never 16 consumer warps, 4 = no chain kernel, 5 = no warp-per-block kernel (nor wave runs), 7 = no wave runs (small panels column by column), 8 = no wide-panel kernel (R > 128 on the row-tiled pipelined kernel), 9 = no column-owning kernel for R <= 128
     int device = 0;
     int num_sms = 0;
     size_t elem = 4;
@@ -510,6 +511,52 @@ struct Engine {
         return true;
     }
 
+    // Mid-size panels (hmm_colown_kernel.cuh): fp32, R % 4 == 0, 32 < R <= 128, reduce sets of one or two blocks, two
+    // CTAs per SM.
+    static bool try_launch_colown(gg_hmm *h, const StepArgs<T> &a, const ColumnPlan &pco, bool fwd, uint32_t nred, uint32_t l2a) {
+        const bool two = nred == 2;
+        const void *k = fwd ? (two ? (const void *)colown_step_kernel<true, true> : (const void *)colown_step_kernel<true, false>)
+                            : (two ? (const void *)colown_step_kernel<false, true> : (const void *)colown_step_kernel<false, false>);
+        configure_once(h->device, 6, [] {
+            for (const void *kk : {(const void *)colown_step_kernel<true, true>, (const void *)colown_step_kernel<true, false>,
+                                   (const void *)colown_step_kernel<false, true>, (const void *)colown_step_kernel<false, false>})
+                GG_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemTma2));
+        });
+        const uint32_t ncls = pco.n_alleles + 1;
+        const uint32_t cw = (a.R + 31u) / 32u;
+        static const uint32_t rh_env = [] { const char *e = std::getenv("GG_COLOWN_RH"); return e ? (uint32_t)std::atoi(e) : 0u; }();
+        uint32_t rh = rh_env ? rh_env : std::max<uint32_t>(1u, std::min<uint32_t>(4u, 8u / cw));
+        while (rh > 1 && cw * rh > kColownMaxWarps) --rh;
+        const uint32_t nload = nred + (fwd ? 1u : 0u);
+        ColownGeom L{};
+        uint32_t stages = 0;
+        for (uint32_t st = std::min<uint32_t>(kTmaMaxStages, nload + 2u); st >= nload + 1u; --st) {
+            L = colown_geom(a.R, st, cw, rh, ncls, fwd);
+            if (L.total <= kMaxDynSmemTma2) { stages = st; break; }
+        }
+        if (!stages) return false;
+        const int threads = 32 * (1 + (int)(cw * rh));
+        auto key = std::make_tuple(k, threads, (size_t)L.total);
+        auto it = h->occ_cache.find(key);
+        int occ;
+        if (it == h->occ_cache.end()) {
+            GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, L.total));
+            h->occ_cache[key] = occ;
+        } else {
+            occ = it->second;
+        }
+        if (occ < 2) return false;
+        const uint64_t n_items = (uint64_t)1 << pco.u;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)h->num_sms * 2);
+        StepArgs<float> af;
+        std::memcpy(&af, &a, sizeof(af));
+        uint32_t ns = stages, cwv = cw, rhv = rh, l2v = l2a;
+        void *params[] = {(void *)&af, (void *)&ns, (void *)&cwv, (void *)&rhv, (void *)&l2v};
+        GG_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(threads), params, L.total, h->stream));
+        ++h->stats.n_launches;
+        return true;
+    }
+
     // Pipelined bulk-copy kernel (hmm_tma_kernel.cuh): fp32, R % 4 == 0, R <= 512.
     static const void *tma_kernel(bool fwd, int V, uint32_t G, int NS, bool mt, int cwt, bool two) {
 #define GG_TMA(VV, GG, NN, MM, CC, TT) if (V == VV && G == GG && NS == NN && mt == MM && cwt == CC && two == TT) return fwd ? (const void *)step_tma_kernel<true, GG, NN, MM, CC, TT, VV> : (const void *)step_tma_kernel<false, GG, NN, MM, CC, TT, VV>;
@@ -552,6 +599,15 @@ struct Engine {
         const uint32_t nred = fwd ? (1u << a.n_free_left) : (1u << (a.u_in - a.n_sh));
         const uint32_t ncls = pco.n_alleles + 1;
         if (a.R > 128 && V == 4 && nred <= 2 && h->kernel_variant != 8 && try_launch_wide(h, a, pco, fwd, nred)) return true;
+        static const uint32_t l2_ahead_env0 = [] {
+            const char *e = std::getenv("GG_L2_AHEAD");
+            return e ? (uint32_t)std::atoi(e) : kTmaL2Ahead;
+        }();
+        static const bool colown_env = [] { const char *e = std::getenv("GG_COLOWN"); return e ? std::atoi(e) != 0 : false; }();
+        const int kv = h->kernel_variant;
+        if (colown_env && a.R > 32 && a.R <= 128 && V == 4 && nred <= 2 && kv != 2 && kv != 3 && kv != 9 &&
+            try_launch_colown(h, a, pco, fwd, nred, l2_ahead_env0))
+            return true;
         // geometry search.  Whole block = one tile (R <= 128): two CTAs of 8 consumer warps per SM when the column's
         // footprint fits twice, else one CTA of 16 (same warp count, deeper ring), else one of 8.  Larger R: row tiles
         // of <= ~40 KB, most consumer warps first, >= 3 stages.
