@@ -525,7 +525,7 @@ struct Engine {
         const uint32_t ncls = pco.n_alleles + 1;
         const uint32_t cw = (a.R + 31u) / 32u;
         static const uint32_t rh_env = [] { const char *e = std::getenv("GG_COLOWN_RH"); return e ? (uint32_t)std::atoi(e) : 0u; }();
-        uint32_t rh = rh_env ? rh_env : std::max<uint32_t>(1u, std::min<uint32_t>(4u, 8u / cw));
+        uint32_t rh = rh_env ? rh_env : std::max<uint32_t>(1u, std::min<uint32_t>(4u, kColownMaxWarps / cw));
         while (rh > 1 && cw * rh > kColownMaxWarps) --rh;
         const uint32_t nload = nred + (fwd ? 1u : 0u);
         ColownGeom L{};
@@ -603,9 +603,12 @@ struct Engine {
             const char *e = std::getenv("GG_L2_AHEAD");
             return e ? (uint32_t)std::atoi(e) : kTmaL2Ahead;
         }();
-        static const bool colown_env = [] { const char *e = std::getenv("GG_COLOWN"); return e ? std::atoi(e) != 0 : false; }();
+        // measured on the R = 88 bench columns (same box, bytes actually moved): backward one-block steps 5.62 -> 5.77
+        // TB/s, two-block reduce sets 4.18 -> 4.76 TB/s; forward 6.03 -> 5.93 TB/s — so the backward step only.
+        // GG_COLOWN: bit 0 = backward, bit 1 = forward
+        static const int colown_env = [] { const char *e = std::getenv("GG_COLOWN"); return e ? std::atoi(e) : 1; }();
         const int kv = h->kernel_variant;
-        if (colown_env && a.R > 32 && a.R <= 128 && V == 4 && nred <= 2 && kv != 2 && kv != 3 && kv != 9 &&
+        if ((colown_env & (fwd ? 2 : 1)) && a.R > 32 && a.R <= 128 && V == 4 && nred <= 2 && kv != 2 && kv != 3 && kv != 9 &&
             try_launch_colown(h, a, pco, fwd, nred, l2_ahead_env0))
             return true;
         // geometry search.  Whole block = one tile (R <= 128): two CTAs of 8 consumer warps per SM when the column's

@@ -17,7 +17,7 @@
 
 namespace gg {
 
-constexpr uint32_t kColownMaxWarps = 12;       // consumer warps: column groups x row interleaves
+constexpr uint32_t kColownMaxWarps = 9;        // consumer warps: column groups x row interleaves (two CTAs per SM at 96 registers; 12 warps at 72 registers measured slower)
 
 struct ColownGeom {
     uint32_t side_off, stage_bytes;

@@ -89,3 +89,13 @@ def test_small_panel_pair_kernel_does_not_spill_at_ten_haplotypes(functions):
         assert "STL" not in text and "LDL" not in text, n
         # the step arguments live in shared memory, so the column pointers are generic: LD.E.128 / ST.E.128
         assert re.search(r"\bLDG?\.E\.128", text) and re.search(r"\bSTG?\.E\.128", text) and "SHFL.BFLY" in text, n
+
+
+def test_column_owning_kernel_for_mid_size_panels(functions):
+    # colown_step_kernel<FWD, TWO> (hmm_colown_kernel.cuh): the backward step of configs[1]'s 88-haplotype panel by default
+    names = [n for n in functions if "colown_step_kernel" in n]
+    assert len(names) == 4
+    for n in names:
+        text = "\n".join(functions[n])
+        assert "UBLKCP" in text and "SYNCS" in text and "LDS.128" in text and "STG.E.128" in text, n
+        assert "STL" not in text and "LDL" not in text, n
