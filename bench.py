@@ -437,7 +437,19 @@ def main():
                 break
             except Exception:
                 pass
-    kernel_name = "chain_kernel" if args.workload == "tagged" else ("pair_wave_kernel" if args.workload == "config1" else ("wide_step_kernel" if args.haps > 128 else "step_tma_kernel"))
+    # the kernel behind the dominant direction (engine.cu picks by panel size: pair_wave_kernel for even panels <= 16,
+    # wide_step_kernel above 128 haplotypes, colown_step_kernel for the backward step of 33..128, step_tma_kernel for the
+    # forward step)
+    if args.workload == "tagged":
+        kernel_name = "chain_kernel"
+    elif args.haps <= 16 and args.haps % 2 == 0:
+        kernel_name = "pair_wave_kernel"
+    elif args.haps > 128:
+        kernel_name = "wide_step_kernel"
+    elif dominant == "backward" and args.haps > 32 and args.haps % 4 == 0 and os.environ.get("GG_COLOWN", "1") != "0":
+        kernel_name = "colown_step_kernel"
+    else:
+        kernel_name = "step_tma_kernel"
     roofline = {
         "bound": "hbm", "kernel": f"step kernel, {dominant} ({kernel_name})", "achieved": ach, "peak": peak, "unit": "GB/s",
         "frac": ach / peak, "box_copy_GBps": box_copy_gbs, "frac_of_box_copy": (ach / box_copy_gbs if box_copy_gbs else None),
