@@ -307,6 +307,31 @@ def test_config4_shape_2pow20_bipartitions():
     assert np.abs(sums - 1.0).max() < 1e-12
 
 
+def test_config4_shape_downscaled_against_oracle_under_the_exact_plan(monkeypatch):
+    # configs[3] down-scaled to what the oracle can walk (R = 12, max-coverage 16: 2^16 blocks per column) with weak
+    # per-read evidence (unsaturated posteriors), run the way the real configuration runs: room for alpha x 2 and
+    # three backward columns, i.e. under the exact planner with the re-created last column.  Against the oracle, and
+    # bit-identical to the everything-fits schedule.
+    from giggles_b200 import fullscale as fs
+    monkeypatch.setenv("GG_EXACT_MIN_COL", "0")
+    p = make_problem(6, 12, region_bp=6 * 124, coverage=60.0, max_coverage=16, read_len_mean=30000.0, read_len_sigma=0.6,
+                     tags="none", window=True, seed=4, base_const=1.1, accuracy=0.8)
+    assert int(p.untagged_per_column().max()) == 16
+    want = oracle.oracle_run(p)
+    assert np.mean((want > 1e-4) & (want < 0.999)) > 0.3
+    base = capi.hmm_run(p, device=0).values
+    assert_posteriors_close(base, want)
+    cb, fb = fs.column_bytes(p.untagged_per_column(), 12, n_alleles=p.n_alleles)
+    budget = int(5.3 * int(cb.max()) + 4 * int(fb.max()) + 8192)
+    dry = capi.schedule_dry_run(cb, fb, budget)
+    assert dry["levels"] >= 2 and dry["n_bwd"] > p.n_columns
+    h = capi.Hmm(p, device=0, budget=budget)
+    h.sweep()
+    assert h.stats()["state_bytes_reserved"] <= budget
+    assert np.array_equal(h.fetch().values, base)
+    h.close()
+
+
 def test_config5_shape_400_haplotypes_multiallelic():
     # configs[4]: 400-haplotype panel (160,000 ordered pairs), 3..16 alleles at every site
     from giggles_b200.synth import config5_window
