@@ -21,15 +21,11 @@ def _bytes(x) -> bytes:
     return x.encode()[:len(x)] if isinstance(x, str) else bytes(x)
 
 
-def edit_distance_batch(pairs, maxdiff=-1, device: int = -1) -> np.ndarray:
-    """``pairs``: sequence of (s, t) (str or bytes).  ``maxdiff``: one int for all pairs or one per pair.
-    Returns int32 distances, pair by pair, exactly what ``giggles.align.edit_distance`` returns for each."""
+def pack_pairs(pairs):
+    """Flatten (s, t) pairs into the C ABI's image: one byte pool (every distinct string once — a read's query is
+    compared against every allele) and per-pair offsets / lengths."""
     pairs = list(pairs)
     n = len(pairs)
-    out = np.zeros(n, dtype=np.int32)
-    if n == 0:
-        return out
-    # every distinct string goes into the pool once (a read's query is compared against every allele)
     index: dict[bytes, tuple[int, int]] = {}
     chunks, pos = [], 0
     s_off = np.empty(n, np.uint64); s_len = np.empty(n, np.uint32)
@@ -42,6 +38,16 @@ def edit_distance_batch(pairs, maxdiff=-1, device: int = -1) -> np.ndarray:
                 pos += len(x)
             arr_off[i], arr_len[i] = index[x]
     pool = np.frombuffer(b"".join(chunks) or b"\0", dtype=np.uint8)
+    return pool, pos, s_off, s_len, t_off, t_len
+
+
+def edit_distance_packed(packed, maxdiff=-1, device: int = -1) -> np.ndarray:
+    """One ``gg_edit_distance_batch`` call on the output of :func:`pack_pairs` (H2D / D2H inside the call)."""
+    pool, pos, s_off, s_len, t_off, t_len = packed
+    n = len(s_off)
+    out = np.zeros(n, dtype=np.int32)
+    if n == 0:
+        return out
     md = np.full(n, int(maxdiff), np.int32) if np.isscalar(maxdiff) else np.ascontiguousarray(maxdiff, dtype=np.int32)
     if md.shape != (n,):
         raise ValueError("maxdiff: one value or one per pair")
@@ -51,6 +57,12 @@ def edit_distance_batch(pairs, maxdiff=-1, device: int = -1) -> np.ndarray:
                                            as_ptr(out, C.c_int32), int(device), err, len(err))
     capi._check(rc, err)
     return out
+
+
+def edit_distance_batch(pairs, maxdiff=-1, device: int = -1) -> np.ndarray:
+    """``pairs``: sequence of (s, t) (str or bytes).  ``maxdiff``: one int for all pairs or one per pair.
+    Returns int32 distances, pair by pair, exactly what ``giggles.align.edit_distance`` returns for each."""
+    return edit_distance_packed(pack_pairs(pairs), maxdiff, device)
 
 
 def edit_distance(s, t, maxdiff: int = -1) -> int:
