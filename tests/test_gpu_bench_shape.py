@@ -116,7 +116,7 @@ np.savez(sys.argv[2], **out)
 print("ok")
 """
 
-COLOWN_SHAPES = ("R88_u11_events", "R128_u10_events")
+COLOWN_SHAPES = ("R88_u11_events",)     # R = 128 runs the default mode in the matrix above
 
 
 def test_column_owning_kernel_modes_against_oracle(tmp_path):
